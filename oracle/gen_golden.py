@@ -1,0 +1,360 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the
+UNMODIFIED reference classes from /root/reference (through oracle/mmcv_shim.py).
+
+Run in the build container (the reference does not exist on the GPU box):
+    python -m oracle.gen_golden
+The fixtures are committed; tests compare (a) the oracle restatement and (b) the
+CUDA path against them.
+"""
+import json
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import mmcv_shim, ver_ref          # noqa: E402
+from vln_ver_b200 import synth                 # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+PC = synth.PC_RANGE
+
+
+def sd_np(module):
+    return {k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+
+
+def perturb(module, seed):
+    """zero-initialised offset/weight projections -> query dependent."""
+    g = torch.Generator().manual_seed(seed)
+    for name, p in module.named_parameters():
+        if name.endswith('sampling_offsets.weight') or name.endswith('attention_weights.weight'):
+            with torch.no_grad():
+                p.add_(torch.randn(p.shape, generator=g) * 0.02)
+
+
+# --------------------------------------------------------------------------- A5
+def gen_msda():
+    vtsa = mmcv_shim.import_reference('bevformer.modules.voxel_temporal_self_attention')
+    ref3d = vtsa.voxel_multi_scale_deformable_attn_pytorch
+    g = torch.Generator().manual_seed(11)
+    cases = {}
+    for name, (Bv, H, W, NH, Dh, Nq, NP) in {
+            'small': (3, 14, 14, 8, 12, 37, 8),
+            'dh96': (2, 14, 14, 8, 96, 19, 8),
+            'rect': (2, 5, 9, 4, 8, 23, 4)}.items():
+        value = torch.randn(Bv, H * W, NH, Dh, generator=g, dtype=torch.float64)
+        loc = torch.rand(Bv, Nq, NH, 1, NP, 2, generator=g, dtype=torch.float64) * 1.6 - 0.3
+        # exact-border and far-outside locations (zero padding, align_corners=False)
+        loc[0, 0, 0, 0, 0] = torch.tensor([0.0, 0.0])
+        loc[0, 0, 0, 0, 1] = torch.tensor([1.0, 1.0])
+        loc[0, 0, 0, 0, 2] = torch.tensor([0.5 / W, 0.5 / H])          # pixel centre (0,0)
+        loc[0, 0, 0, 0, 3] = torch.tensor([-3.0, 7.0])
+        loc[0, 1, 0, 0, 0] = torch.tensor([(W - 0.5) / W, (H - 0.5) / H])  # last pixel centre
+        w = torch.rand(Bv, Nq, NH, 1, NP, generator=g, dtype=torch.float64)
+        w = w / w.sum(-1, keepdim=True)
+        gout = torch.randn(Bv, Nq, NH * Dh, generator=g, dtype=torch.float64)
+        value.requires_grad_(True); loc.requires_grad_(True); w.requires_grad_(True)
+        # reference-owned 3-D sampler at depth 1 (z = 0.5 -> grid z = 0)
+        loc3 = torch.cat([loc, torch.full_like(loc[..., :1], 0.5)], -1)
+        out3 = ref3d(value, [(1, H, W)], loc3, w)
+        out2 = ver_ref.multi_scale_deformable_attn_pytorch(
+            value, torch.tensor([[H, W]]), loc, w)
+        assert (out3 - out2).abs().max().item() < 1e-12, (out3 - out2).abs().max()
+        gv, gl, gw = torch.autograd.grad(out3, (value, loc, w), gout)
+        cases.update({
+            f'{name}.value': value.detach().numpy().astype(np.float32),
+            f'{name}.shape': np.array([H, W], np.int64),
+            f'{name}.loc': loc.detach().numpy().astype(np.float32),
+            f'{name}.w': w.detach().numpy().astype(np.float32),
+            f'{name}.gout': gout.numpy().astype(np.float32),
+        })
+        # golden outputs recomputed in fp64 from the fp32-rounded inputs so the
+        # fixture is self-consistent
+        v32 = torch.from_numpy(cases[f'{name}.value']).double().requires_grad_(True)
+        l32 = torch.from_numpy(cases[f'{name}.loc']).double().requires_grad_(True)
+        w32 = torch.from_numpy(cases[f'{name}.w']).double().requires_grad_(True)
+        g32 = torch.from_numpy(cases[f'{name}.gout']).double()
+        l3 = torch.cat([l32, torch.full_like(l32[..., :1], 0.5)], -1)
+        o = ref3d(v32, [(1, H, W)], l3, w32)
+        gv, gl, gw = torch.autograd.grad(o, (v32, l32, w32), g32)
+        cases.update({f'{name}.out': o.detach().numpy(), f'{name}.gvalue': gv.numpy(),
+                      f'{name}.gloc': gl.numpy(), f'{name}.gw': gw.numpy()})
+    np.savez_compressed(os.path.join(OUT, 'msda_cases.npz'), **cases)
+    print('msda_cases ok')
+
+
+# --------------------------------------------------------------------------- A1 / A2
+def run_unmodified_point_sampling(enc_mod, bev_z, bev_h, bev_w, l2i6, shift, num_points_in_voxel=4):
+    """Calls the UNMODIFIED VoxelFormerEncoder.point_sampling (reads the literal
+    'path to/...' files, M/voxel_encoder.py:122,133) from a temp cwd."""
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, 'path to', 'camera_parameters', 'world2pixel'))
+        scan, vp = 'scanA', 'vp0'
+        data = {f'{vp}_i1_{d}': l2i6[d].astype(np.float64).tolist() for d in range(6)}
+        with open(os.path.join(td, 'path to', 'camera_parameters', 'world2pixel', scan + '.json'), 'w') as f:
+            json.dump(data, f)
+        with open(os.path.join(td, 'path to', 'scanvp2cord.pkl'), 'wb') as f:
+            pickle.dump({scan + '_' + vp: [float(x) for x in shift]}, f)
+        os.chdir(td)
+        try:
+            Enc = enc_mod.VoxelFormerEncoder
+            ref_3d = Enc.get_reference_points(bev_z, bev_h, bev_w, num_points_in_voxel, dim='3d',
+                                              bs=1, device='cpu', dtype=torch.float32)
+            dummy = type('E', (), {})()
+            rpc, mask = Enc.point_sampling(dummy, ref_3d, PC, [dict(sample_idx=f'{scan}_{vp}')])
+        finally:
+            os.chdir(cwd)
+    return ref_3d, rpc, mask
+
+
+def gen_point_sampling(enc_mod):
+    out = {}
+    for tag, grid, seed in [('g4x15x15', (4, 15, 15), 21), ('g8x20x20', (8, 20, 20), 22)]:
+        l2i, sh = synth.make_rig(1, 6, grid, seed=seed)
+        ref_3d, rpc, mask = run_unmodified_point_sampling(enc_mod, *grid, l2i[0], sh[0])
+        # restatement must agree bit for bit
+        r2 = ver_ref.get_reference_points_3d(*grid)
+        assert torch.equal(r2, ref_3d)
+        rpc2, mask2 = ver_ref.point_sampling(r2, PC, torch.from_numpy(l2i[0]), torch.from_numpy(sh[0]))
+        assert torch.equal(rpc, rpc2) and torch.equal(mask, mask2)
+        idx = ver_ref.visible_indexes(mask)
+        out.update({f'{tag}.lidar2img': l2i, f'{tag}.originshift': sh,
+                    f'{tag}.ref_3d': ref_3d.numpy(), f'{tag}.rpc': rpc.numpy(),
+                    f'{tag}.mask': mask.numpy(),
+                    f'{tag}.index_len': np.array([len(i) for i in idx], np.int64),
+                    f'{tag}.index_cat': torch.cat(idx).numpy().astype(np.int64)})
+    np.savez_compressed(os.path.join(OUT, 'point_sampling_6cam.npz'), **out)
+    print('point_sampling ok')
+
+
+# --------------------------------------------------------------------------- A3 / A4
+def gen_sca(sca_mod):
+    out = {}
+    for tag, ncam, grid, C, seed in [('c6', 6, (4, 15, 15), 96, 31), ('c18', 18, (4, 10, 10), 96, 32)]:
+        torch.manual_seed(seed)
+        m = sca_mod.SpatialCrossAttention(
+            embed_dims=C, num_cams=ncam, pc_range=PC, dropout=0.1, batch_first=True,
+            deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                      num_points=8, num_levels=1)).eval()
+        perturb(m, seed + 100)
+        l2i, sh = synth.make_rig(1, ncam, grid, seed=seed)
+        rpc, mask = ver_ref.point_sampling_batched(*grid, PC, torch.from_numpy(l2i), torch.from_numpy(sh))
+        Nq = grid[0] * grid[1] * grid[2]
+        query = torch.randn(1, Nq, C)
+        value = torch.randn(ncam, 196, 1, C) * 0.5
+        ss = torch.tensor([[14, 14]])
+        with torch.no_grad():
+            y = m(query, value, value, reference_points_cam=rpc, bev_mask=mask,
+                  spatial_shapes=ss, level_start_index=torch.tensor([0]))
+            sd = {k: v for k, v in m.state_dict().items()}
+            y2 = ver_ref.sca_forward(sd, '', query, value, rpc, mask, ss)
+        assert torch.allclose(y, y2, atol=1e-6), (y - y2).abs().max()
+        out.update({f'{tag}.query': query.numpy(), f'{tag}.value': value.numpy(),
+                    f'{tag}.lidar2img': l2i, f'{tag}.originshift': sh,
+                    f'{tag}.grid': np.array(grid), f'{tag}.out': y.numpy()})
+        out.update({f'{tag}.sd.{k}': v for k, v in sd_np(m).items()})
+    np.savez_compressed(os.path.join(OUT, 'sca.npz'), **out)
+    print('sca ok')
+
+
+# --------------------------------------------------------------------------- A6 / A7
+def encoder_cfg(C, ffn, num_layers=3):
+    return dict(
+        type='VoxelFormerEncoder', num_layers=num_layers, pc_range=PC, num_points_in_voxel=4,
+        return_intermediate=False,
+        transformerlayers=dict(
+            type='VoxelFormerLayer',
+            attn_cfgs=[dict(type='SpatialCrossAttention', pc_range=PC,
+                            deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                      num_points=8, num_levels=1),
+                            embed_dims=C)],
+            ffn_cfgs=dict(type='FFN', embed_dims=C, feedforward_channels=1024, num_fcs=2,
+                          ffn_drop=0., act_cfg=dict(type='ReLU', inplace=True)),
+            feedforward_channels=ffn, ffn_dropout=0.1,
+            operation_order=('cross_attn', 'norm', 'ffn', 'norm')))
+
+
+def run_unmodified_encoder(enc, bev_query, value, grid, l2i6, shift, bev_pos):
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, 'path to', 'camera_parameters', 'world2pixel'))
+        data = {f'vp0_i1_{d}': l2i6[d].astype(np.float64).tolist() for d in range(6)}
+        with open(os.path.join(td, 'path to', 'camera_parameters', 'world2pixel', 'scanA.json'), 'w') as f:
+            json.dump(data, f)
+        with open(os.path.join(td, 'path to', 'scanvp2cord.pkl'), 'wb') as f:
+            pickle.dump({'scanA_vp0': [float(x) for x in shift]}, f)
+        os.chdir(td)
+        try:
+            with torch.no_grad():
+                y = enc(bev_query, value, value, bev_z=grid[0], bev_h=grid[1], bev_w=grid[2],
+                        bev_pos=bev_pos, spatial_shapes=torch.tensor([[14, 14]]),
+                        level_start_index=torch.tensor([0]), prev_bev=None,
+                        shift=bev_query.new_tensor([[0., 0., 0.]]),
+                        img_metas=[dict(sample_idx='scanA_vp0')])
+        finally:
+            os.chdir(cwd)
+    return y
+
+
+def gen_encoder():
+    C, grid, seed = 96, (4, 15, 15), 41
+    torch.manual_seed(seed)
+    enc = mmcv_shim.build_transformer_layer_sequence(encoder_cfg(C, 2 * C)).eval()
+    for p in enc.parameters():
+        if p.dim() > 1:
+            torch.nn.init.xavier_uniform_(p)
+    for m in enc.modules():
+        if type(m).__name__ == 'MSDeformableAttention3D':
+            m.init_weights()
+    perturb(enc, seed + 100)
+    Nq = grid[0] * grid[1] * grid[2]
+    l2i, sh = synth.make_rig(1, 6, grid, seed=seed)
+    bev_query = torch.randn(Nq, 1, C)
+    value = torch.randn(6, 196, 1, C) * 0.5
+    bev_pos = torch.zeros(Nq, 1, C)
+    y = run_unmodified_encoder(enc, bev_query, value, grid, l2i[0], sh[0], bev_pos)
+    sd = dict(enc.state_dict())
+    y2 = ver_ref.encoder_forward(sd, '', bev_query, value, *grid, PC, torch.from_numpy(l2i),
+                                 torch.from_numpy(sh), torch.tensor([[14, 14]]))
+    assert torch.allclose(y, y2, atol=2e-6), (y - y2).abs().max()
+    out = {'bev_query': bev_query.numpy(), 'value': value.numpy(), 'lidar2img': l2i,
+           'originshift': sh, 'grid': np.array(grid), 'out': y.numpy()}
+    out.update({f'sd.{k}': v for k, v in sd_np(enc).items()})
+    np.savez_compressed(os.path.join(OUT, 'encoder_6cam_c96.npz'), **out)
+    print('encoder ok')
+
+
+# --------------------------------------------------------------------------- A8
+def gen_transformer():
+    """Unmodified VoxelPerceptionTransformer.get_voxel_features at its literal
+    (6, 1, 14, 14, 768) shape.  Weights are NOT stored (44 MB): they are regenerated
+    from `manual_seed(seed)` + the reference's own init_weights + perturb(); the
+    fixture holds inputs' seeds and a row-subsampled output."""
+    vt = mmcv_shim.import_reference('bevformer.modules.voxel_transformer')
+    C, grid, seed = 768, (4, 15, 15), 51
+    torch.manual_seed(seed)
+    tr = vt.VoxelPerceptionTransformer(
+        num_cams=6, embed_dims=C, rotate_prev_bev=True, use_shift=True, use_can_bus=True,
+        decoder_on_bev=False, encoder=encoder_cfg(C, 2 * C), decoder=None).eval()
+    tr.init_weights()
+    perturb(tr, seed + 100)
+    Nq = grid[0] * grid[1] * grid[2]
+    l2i, sh = synth.make_rig(1, 6, grid, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    feats = torch.randn(6, 1, 196, C, generator=g) * 0.5
+    bev_queries = torch.randn(Nq, C, generator=g)
+    bev_pos = torch.zeros(1, C, *grid)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, 'path to', 'camera_parameters', 'world2pixel'))
+        data = {f'vp0_i1_{d}': l2i[0, d].astype(np.float64).tolist() for d in range(6)}
+        with open(os.path.join(td, 'path to', 'camera_parameters', 'world2pixel', 'scanA.json'), 'w') as f:
+            json.dump(data, f)
+        with open(os.path.join(td, 'path to', 'scanvp2cord.pkl'), 'wb') as f:
+            pickle.dump({'scanA_vp0': [float(x) for x in sh[0]]}, f)
+        os.chdir(td)
+        try:
+            with torch.no_grad():
+                y = tr.get_voxel_features(feats, bev_queries, *grid, bev_pos=bev_pos,
+                                          img_metas=[dict(sample_idx='scanA_vp0')])
+        finally:
+            os.chdir(cwd)
+    sd = dict(tr.state_dict())
+    with torch.no_grad():
+        y2 = ver_ref.get_voxel_features(sd, '', feats, bev_queries, *grid, PC,
+                                        torch.from_numpy(l2i), torch.from_numpy(sh))
+    assert torch.allclose(y, y2, atol=5e-6), (y - y2).abs().max()
+    rows = np.arange(0, Nq, 7)
+    np.savez_compressed(
+        os.path.join(OUT, 'transformer_6cam_c768.npz'), seed=np.array(seed), grid=np.array(grid),
+        lidar2img=l2i, originshift=sh, rows=rows, out_rows=y[0, rows].numpy(),
+        out_abs_sum=np.array(y.double().abs().sum().item()))
+    print('transformer ok')
+    return tr, sd
+
+
+# --------------------------------------------------------------------------- A9 / A10 / A12
+def gen_head():
+    pe = mmcv_shim.import_reference('bevformer.modules.voxel_positional_embedding')
+    mmcv_shim.import_reference('bevformer.modules.voxel_transformer')
+    hd = mmcv_shim.import_reference('bevformer.dense_heads.voxelformer_occupancy_head')
+    C, grid, seed = 32, (4, 6, 6), 61
+    occ_size = [12.0 / grid[2], 12.0 / grid[1], 3.5 / grid[0]]      # bev_z == occ_zdim branch
+    out = {}
+    for tag, osz in [('pervoxel', occ_size), ('column', [2.0, 2.0, 0.5])]:
+        torch.manual_seed(seed)
+        head = hd.VoxelFormerOccupancyHead(
+            bev_h=grid[1], bev_w=grid[2], bev_z=grid[0], num_query=10, num_classes=17, in_channels=C,
+            sync_cls_avg_factor=True, with_box_refine=True, as_two_stage=False,
+            point_cloud_range=PC, occupancy_size=osz, occ_dims=16, occupancy_classes=16,
+            only_occ=True, only_det=False, refine_occ=False,
+            transformer=mmcv_shim.ConfigDict(
+                type='VoxelPerceptionTransformer', num_cams=6, embed_dims=C,
+                encoder=encoder_cfg(C, 2 * C, num_layers=1), decoder=None),
+            bbox_coder=dict(type='NMSFreeCoder', pc_range=PC, max_num=50, num_classes=17),
+            positional_encoding=dict(type='VoxelLearnedPositionalEncoding', num_feats=C // 2,
+                                     row_num_embed=grid[1], col_num_embed=grid[2], z_num_embed=grid[0]),
+            loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+            loss_bbox=dict(type='L1Loss', loss_weight=0.25),
+            loss_iou=dict(type='GIoULoss', loss_weight=0.0),
+            loss_occupancy=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25,
+                                loss_weight=1.0)).eval()
+        Nq = grid[0] * grid[1] * grid[2]
+        bev_embed = torch.randn(1, Nq, C)
+
+        class _Stub(torch.nn.Module):          # the head only consumes get_voxel_features()
+            decoder = None
+
+            def get_voxel_features(self, *a, **k):
+                return bev_embed
+        head.transformer = _Stub()
+        with torch.no_grad():
+            outs = head(torch.zeros(6, 1, 196, C), [dict(sample_idx='scanA_vp0')])
+            pos = head.positional_encoding(torch.zeros(1, *grid))
+            logits = outs['occupancy_preds']
+            # make some voxels occupied for the decode test
+            logits = logits + torch.randn_like(logits) * 3.0
+            dec = head.get_occupancy_prediction(dict(occupancy_preds=logits.clone(), flow_preds=None))
+        sd = {k: v for k, v in head.state_dict().items()}
+        y2 = ver_ref.occ_head(sd, '', bev_embed, *grid, head.occ_xdim, head.occ_ydim, head.occ_zdim,
+                              occ_dims=16, refine_occ=False, only_occ=True)
+        assert torch.allclose(outs['occupancy_preds'], y2, atol=1e-6)
+        pos2 = ver_ref.positional_encoding(sd, 'positional_encoding.', 1, *grid)
+        assert torch.equal(pos, pos2)
+        dec2 = ver_ref.get_occupancy_prediction(logits)
+        assert torch.equal(dec['occupancy_preds'], dec2)
+        keep = {k: v.numpy() for k, v in sd.items()
+                if k.startswith(('occ_', 'positional_encoding', 'voxel_embedding'))}
+        out.update({f'{tag}.bev_embed': bev_embed.numpy(), f'{tag}.grid': np.array(grid),
+                    f'{tag}.occ_dims3': np.array([head.occ_xdim, head.occ_ydim, head.occ_zdim]),
+                    f'{tag}.occupancy_preds': outs['occupancy_preds'].numpy(),
+                    f'{tag}.pos': pos.numpy(), f'{tag}.decode_logits': logits.numpy(),
+                    f'{tag}.decode': dec['occupancy_preds'].numpy()})
+        out.update({f'{tag}.sd.{k}': v for k, v in keep.items()})
+    np.savez_compressed(os.path.join(OUT, 'head.npz'), **out)
+    print('head ok')
+
+
+def main():
+    assert mmcv_shim.reference_available(), 'needs /root/reference'
+    os.makedirs(OUT, exist_ok=True)
+    mmcv_shim.install()
+    sca_mod = mmcv_shim.import_reference('bevformer.modules.spatial_cross_attention')
+    enc_mod = mmcv_shim.import_reference('bevformer.modules.voxel_encoder')
+    gen_msda()
+    gen_point_sampling(enc_mod)
+    gen_sca(sca_mod)
+    gen_encoder()
+    gen_transformer()
+    gen_head()
+
+
+if __name__ == '__main__':
+    main()
