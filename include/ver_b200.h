@@ -1,0 +1,170 @@
+/* libver_b200.so -- C ABI of the B200-native (sm_100a) implementation of VER's
+ * 2D->3D volumetric lifting hot path.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory unless the parameter is documented "host";
+ *   - the caller owns every buffer; the library never allocates, frees or
+ *     synchronises; all work is enqueued on `stream` (a cudaStream_t);
+ *   - return value: 0 = VER_OK, negative = error; ver_last_error() returns a
+ *     thread-local message for the last failing call on this thread;
+ *   - functions are re-entrant; one call per stream at a time is the caller's
+ *     responsibility;
+ *   - dtype: VER_F32 (=0) or VER_F16 (=1) selects the storage type of `value`
+ *     feature maps and of sampled outputs; sampling locations, attention
+ *     weights/logits, camera geometry and all accumulation are always fp32
+ *     (the reference force-casts to fp32 at
+ *     projects/mmdet3d_plugin/bevformer/modules/multi_scale_deformable_attn_function.py:93
+ *     and runs SCA under @force_fp32, .../spatial_cross_attention.py:76).
+ *
+ * Path shorthands used in the citations below (under the reference root):
+ *   M/   = projects/mmdet3d_plugin/bevformer/modules/
+ *   HEAD = projects/mmdet3d_plugin/bevformer/dense_heads/voxelformer_occupancy_head.py
+ */
+#ifndef VER_B200_H_
+#define VER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VER_OK 0
+#define VER_ERR_INVALID_ARG (-1)
+#define VER_ERR_CUDA (-2)
+#define VER_ERR_UNSUPPORTED (-3)
+
+#define VER_F32 0
+#define VER_F16 1
+
+typedef void* ver_stream_t; /* cudaStream_t */
+
+/* ABI version of this header (bumped on any signature change). */
+int ver_abi_version(void);
+/* Thread-local message of the last failing call ("" if none). */
+const char* ver_last_error(void);
+/* Number of kernels this library has launched in this process (all threads);
+ * bench.py reports the delta over the timed region as `gpu_launches`. */
+int64_t ver_launch_count(void);
+
+/* ---------------------------------------------------------------- A1 + A2
+ * Replaces VoxelFormerEncoder.get_reference_points(dim='3d') (M/voxel_encoder.py:53-83)
+ * and the arithmetic of VoxelFormerEncoder.point_sampling (M/voxel_encoder.py:136-195)
+ * for B panoramas at once.  Voxel n = z*(H*W) + h*W + w, reference point
+ * ((w+.5)/W, (h+.5)/H, (z+.5)/Z); world = ref*range + pc_min + originshift;
+ * cam = lidar2img @ [world,1] with the fp32 summation order ((m0*x+m1*y)+m2*z)+m3
+ * and no FMA contraction (bit-exact to torch's CPU matmul); mask = z>1e-5 &
+ * 0<u<1 & 0<v<1 with u = x/max(z,1e-5)/img_w, v = y/max(z,1e-5)/img_h.
+ *   lidar2img  [B, Ncam, 4, 4] fp32 row-major      originshift [B, 3] fp32
+ *   pc_range   host, 6 doubles (x0,y0,z0,x1,y1,z1) -- doubles because the reference subtracts
+ *              the Python floats before rounding to fp32 (M/voxel_encoder.py:146-151)
+ *   rpc        [Ncam, B, Nq, 1, 2] fp32 (reference_points_cam)     (out)
+ *   mask       [Ncam, B, Nq, 1] uint8 0/1 (bev_mask, torch.bool)   (out)
+ *   vis_bits   [B, Nq] uint32, bit c = mask[c,b,n]; may be NULL; requires Ncam<=32 (out)
+ *   count      [B, Nq] int32 = number of cameras seeing the voxel; may be NULL (out) */
+int ver_point_sampling_f32(const float* lidar2img, const float* originshift, const double* pc_range,
+                           int B, int Ncam, int Z, int H, int W, float img_w, float img_h,
+                           float* rpc, uint8_t* mask, uint32_t* vis_bits, int32_t* count,
+                           ver_stream_t stream);
+
+/* ---------------------------------------------------------------- K8 (index tensors)
+ * Replaces the per-camera `mask.sum(-1).nonzero()` + Python max(len) of
+ * SpatialCrossAttention.forward (M/spatial_cross_attention.py:138-142) without a
+ * host sync: for every (b, cam) the ascending list of visible voxel ids.
+ *   mask    [Ncam, B, Nq] uint8
+ *   counts  [B, Ncam] int32 (out)      index [B, Ncam, Nq] int32, entries >= count are -1 (out) */
+int ver_visible_index(const uint8_t* mask, int B, int Ncam, int Nq, int32_t* counts,
+                      int32_t* index, ver_stream_t stream);
+
+/* ---------------------------------------------------------------- A5 (operator boundary B2)
+ * Replaces mmcv._ext.ms_deform_attn_forward as called at
+ * M/multi_scale_deformable_attn_function.py:118-124.
+ *   value  [Bv, S, NH, Dh] dtype, S = sum_l h_l*w_l        shapes_hw host int32 [NL,2] = (h,w)
+ *   loc    [Bv, Nq, NH, NL, NP, 2] fp32 (x,y) in [0,1]     w [Bv, Nq, NH, NL, NP] fp32
+ *   out    [Bv, Nq, NH*Dh] dtype
+ * zero padding, align_corners=False (pixel = loc*size - 0.5). */
+int ver_msda_forward(int dtype, const void* value, const int32_t* shapes_hw, int NL, const float* loc,
+                     const float* w, void* out, int Bv, int S, int NH, int Dh, int Nq, int NP,
+                     ver_stream_t stream);
+
+/* Replaces mmcv._ext.ms_deform_attn_backward (M/multi_scale_deformable_attn_function.py:150-160).
+ *   grad_out [Bv, Nq, NH*Dh] dtype
+ *   grad_value [Bv, S, NH, Dh] fp32, grad_loc like loc, grad_w like w: all three are
+ *   OVERWRITTEN (the reference passes zero-filled buffers, :146-148; no pre-zeroing needed). */
+int ver_msda_backward(int dtype, const void* value, const int32_t* shapes_hw, int NL, const float* loc,
+                      const float* w, const void* grad_out, float* grad_value, float* grad_loc,
+                      float* grad_w, int Bv, int S, int NH, int Dh, int Nq, int NP,
+                      ver_stream_t stream);
+
+/* ---------------------------------------------------------------- A3 (+) A4 (+) A5 fused
+ * The sampling part of SpatialCrossAttention.forward (M/spatial_cross_attention.py:138-173)
+ * with MSDeformableAttention3D's softmax / location arithmetic (:340-374) fused in, for
+ * num_levels = 1 and num_Z_anchors = 1:
+ *   slots[b,n,:] = 1/max(count,1) * sum_{cam visible, ascending} sum_p softmax(aw)[p] *
+ *                  bilinear(value[b*Ncam+cam], rpc[cam,b,n] + offs[p]/(Sw,Sh))
+ * i.e. the tensor handed to output_proj (:174).  Never materialises the padded rebatch.
+ *   value   [B*Ncam, Sh*Sw, NH, Dh] dtype (already value_proj'ed)
+ *   logits  [B*Nq, ld] fp32: columns [0, NH*NP*2) = sampling_offsets Linear output
+ *           (layout (h, p, xy), :340-341), columns [NH*NP*2, NH*NP*3) = attention_weights
+ *           Linear output BEFORE softmax (layout (h, p), :342-343)
+ *   rpc, vis_bits from ver_point_sampling_f32          slots [B, Nq, NH*Dh] dtype (out)
+ * Requires Ncam <= 32, NP == 8, Dh % 8 == 0 (else VER_ERR_UNSUPPORTED). */
+int ver_sca_forward(int dtype, const void* value, const float* logits, int ld_logits, const float* rpc,
+                    const uint32_t* vis_bits, void* slots, int B, int Ncam, int Z, int H, int W,
+                    int Sh, int Sw, int NH, int Dh, int NP, ver_stream_t stream);
+
+/* Backward of ver_sca_forward.
+ *   grad_slots  [B, Nq, NH*Dh] dtype
+ *   grad_value  [B*Ncam, Sh*Sw, NH, Dh] fp32 (overwritten)
+ *   grad_logits [B*Nq, ld] fp32, columns [0, NH*NP*3) overwritten
+ *   counts/index from ver_visible_index (camera-major hit lists) */
+int ver_sca_backward(int dtype, const void* value, const float* logits, int ld_logits,
+                     const float* rpc, const uint32_t* vis_bits, const int32_t* counts,
+                     const int32_t* index, const void* grad_slots, float* grad_value,
+                     float* grad_logits, int B, int Ncam, int Z, int H, int W, int Sh, int Sw,
+                     int NH, int Dh, int NP, ver_stream_t stream);
+
+/* ---------------------------------------------------------------- A8 prologue
+ * feat + cams_embeds[cam] + level_embeds[0] and the (Ncam,B,S,C) -> (B*Ncam,S,C) reorder of
+ * VoxelPerceptionTransformer.get_voxel_features (M/voxel_transformer.py:146-168) followed by
+ * SpatialCrossAttention's value.permute(2,0,1,3).reshape (M/spatial_cross_attention.py:158-161).
+ *   feats [Ncam, B, S, C] fp32   cams_embeds [Ncam, C] fp32 or NULL   level_embed [C] fp32
+ *   out   [B*Ncam, S, C] dtype */
+int ver_feat_embed(int dtype, const float* feats, const float* cams_embeds, const float* level_embed,
+                   void* out, int Ncam, int B, int S, int C, ver_stream_t stream);
+
+/* ---------------------------------------------------------------- A6 epilogue
+ * y = LayerNorm(x + residual) * gamma + beta, eps inside sqrt, over the last dim C
+ * (the 'norm' steps of VoxelFormerLayer.forward, M/voxel_encoder.py:435-437, fused with the
+ * residual adds of SCA (:176 of spatial_cross_attention.py) and of mmcv FFN).
+ *   x, residual (may be NULL), y: [rows, C] dtype; gamma, beta fp32 [C] */
+int ver_add_layernorm(int dtype, const void* x, const void* residual, const float* gamma,
+                      const float* beta, void* y, int64_t rows, int C, float eps,
+                      ver_stream_t stream);
+
+/* ---------------------------------------------------------------- A11
+ * Sigmoid focal loss of mmdet FocalLoss(use_sigmoid=True) (vocc.py:190-195; calls HEAD:981,
+ * HEAD:1425) with the dense target built on the fly from the sparse GT
+ * (HEAD:1326-1330): target[n] = classes ("empty") unless listed in occ_gt.
+ *   logits [N, Ccls] fp32      dense_gt [N] int32 scratch (out; filled by this call)
+ *   occ_gt [n_gt, 2] int64 (flat index, class); n_gt < 0 means "dense_gt is an INPUT holding
+ *          ready-made class targets in [0, Ccls]" (the generic FocalLoss.forward(pred, target) call)
+ *   loss_sum fp32[1] = sum of element losses (out, overwritten); num_pos int32[1] (out)
+ *   grad_logits [N, Ccls] fp32 = d(loss_sum)/d(logits) or NULL */
+int ver_focal_loss(const float* logits, const int64_t* occ_gt, int n_gt, int32_t* dense_gt,
+                   float* loss_sum, int32_t* num_pos, float* grad_logits, int64_t N, int Ccls,
+                   float gamma, float alpha, ver_stream_t stream);
+
+/* ---------------------------------------------------------------- A12
+ * get_occupancy_prediction (HEAD:1505-1524): class = argmax([sigmoid(logits), thr]);
+ * rows with class < Ccls are emitted in ascending row order.
+ *   logits [N, Ccls] fp32     out_pairs [N, 2] int64 capacity (index, class) (out)
+ *   out_count int32[1] (out)  scratch: int32 [ceil(N/1024) + 1] */
+int ver_occupancy_decode(const float* logits, int64_t N, int Ccls, float threshold,
+                         int64_t* out_pairs, int32_t* out_count, int32_t* scratch,
+                         ver_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VER_B200_H_ */

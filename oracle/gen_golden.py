@@ -137,7 +137,7 @@ def gen_point_sampling(enc_mod):
 # --------------------------------------------------------------------------- A3 / A4
 def gen_sca(sca_mod):
     out = {}
-    for tag, ncam, grid, C, seed in [('c6', 6, (4, 15, 15), 96, 31), ('c18', 18, (4, 10, 10), 96, 32)]:
+    for tag, ncam, grid, C, seed in [('c6', 6, (4, 15, 15), 256, 31), ('c18', 18, (4, 10, 10), 256, 32)]:
         torch.manual_seed(seed)
         m = sca_mod.SpatialCrossAttention(
             embed_dims=C, num_cams=ncam, pc_range=PC, dropout=0.1, batch_first=True,
@@ -204,9 +204,9 @@ def run_unmodified_encoder(enc, bev_query, value, grid, l2i6, shift, bev_pos):
 
 
 def gen_encoder():
-    C, grid, seed = 96, (4, 15, 15), 41
+    C, grid, seed = 256, (4, 15, 15), 41
     torch.manual_seed(seed)
-    enc = mmcv_shim.build_transformer_layer_sequence(encoder_cfg(C, 2 * C)).eval()
+    enc = mmcv_shim.build_transformer_layer_sequence(encoder_cfg(C, C, num_layers=2)).eval()
     for p in enc.parameters():
         if p.dim() > 1:
             torch.nn.init.xavier_uniform_(p)
@@ -222,12 +222,12 @@ def gen_encoder():
     y = run_unmodified_encoder(enc, bev_query, value, grid, l2i[0], sh[0], bev_pos)
     sd = dict(enc.state_dict())
     y2 = ver_ref.encoder_forward(sd, '', bev_query, value, *grid, PC, torch.from_numpy(l2i),
-                                 torch.from_numpy(sh), torch.tensor([[14, 14]]))
+                                 torch.from_numpy(sh), torch.tensor([[14, 14]]), num_layers=2)
     assert torch.allclose(y, y2, atol=2e-6), (y - y2).abs().max()
     out = {'bev_query': bev_query.numpy(), 'value': value.numpy(), 'lidar2img': l2i,
            'originshift': sh, 'grid': np.array(grid), 'out': y.numpy()}
     out.update({f'sd.{k}': v for k, v in sd_np(enc).items()})
-    np.savez_compressed(os.path.join(OUT, 'encoder_6cam_c96.npz'), **out)
+    np.savez_compressed(os.path.join(OUT, 'encoder_6cam_c256.npz'), **out)
     print('encoder ok')
 
 

@@ -1,0 +1,308 @@
+"""GPU tier (B200): the CUDA path, called through the C ABI (vln_ver_b200.ops -> ctypes ->
+libver_b200.so), against (a) the committed golden vectors from the unmodified reference and
+(b) the CPU oracle on seeded inputs.  Tolerances (BASELINE.json north_star): max-norm relative
+error <= 1e-5 for fp32, <= 1e-3 for fp16 storage, bit-exact for masks / index tensors."""
+import numpy as np
+import pytest
+import torch
+
+import vln_ver_b200 as V
+from oracle import ver_ref
+from vln_ver_b200 import ops, synth
+from vln_ver_b200.config import per_voxel_occupancy_size
+from conftest import load_golden, rel_err, sub
+
+pytestmark = pytest.mark.gpu
+PC = synth.PC_RANGE
+DEV = 'cuda'
+TOL = {torch.float32: 1e-5, torch.float16: 1e-3}
+
+
+def cuda(t):
+    return t.to(DEV)
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+# ------------------------------------------------------------------ A1 / A2 / K8
+def check_geometry(l2i, sh, grid, rpc_ref, mask_ref):
+    rpc, mask, bits, count = ops.point_sampling(cuda(l2i), cuda(sh), PC, *grid)
+    assert torch.equal(mask.cpu(), mask_ref), 'visibility mask must be bit-exact'
+    assert torch.equal(rpc.cpu(), rpc_ref), 'reference_points_cam must be bit-exact'
+    m = mask_ref[..., 0]
+    assert torch.equal(count.cpu().long(), m.sum(0))
+    shifts = torch.arange(m.shape[0]).view(-1, 1, 1)
+    assert torch.equal(bits.cpu().long() & 0xffffffff, (m.long() << shifts).sum(0))
+    counts, index = ops.visible_index(mask)
+    counts, index = counts.cpu(), index.cpu()
+    for b in range(m.shape[1]):
+        ref_idx = ver_ref.visible_indexes(mask_ref[:, b:b + 1])
+        for c, ri in enumerate(ref_idx):
+            assert counts[b, c].item() == len(ri)
+            assert torch.equal(index[b, c, :len(ri)].long(), ri)
+            assert (index[b, c, len(ri):] == -1).all()
+
+
+def test_point_sampling_golden_bit_exact():
+    g = load_golden('point_sampling_6cam.npz')
+    for tag, grid in (('g4x15x15', (4, 15, 15)), ('g8x20x20', (8, 20, 20))):
+        c = sub(g, tag)
+        check_geometry(c['lidar2img'], c['originshift'], grid, c['rpc'], c['mask'])
+
+
+@pytest.mark.parametrize('ncam,B,grid', [(18, 3, (16, 40, 40)), (6, 2, (4, 15, 15)), (18, 2, (3, 5, 7))])
+def test_point_sampling_batched_vs_oracle(ncam, B, grid):
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=5)
+    l2i, sh = torch.from_numpy(l2i), torch.from_numpy(sh)
+    rpc_ref, mask_ref = ver_ref.point_sampling_batched(*grid, PC, l2i, sh)
+    check_geometry(l2i, sh, grid, rpc_ref, mask_ref)
+
+
+def test_all_cameras_blind():
+    """cameras looking away from the grid: empty index lists, count clamp -> zero slots."""
+    grid = (2, 4, 8)
+    l2i = torch.from_numpy(np.stack([synth.camera_matrix(0, 0, [100., 0., 0.])] * 6)[None].astype(np.float32))
+    sh = torch.zeros(1, 3)
+    rpc, mask, bits, count = ops.point_sampling(cuda(l2i), cuda(sh), PC, *grid)
+    assert not mask.any() and (count == 0).all()
+    counts, index = ops.visible_index(mask)
+    assert (counts == 0).all() and (index == -1).all()
+    vis = ops.Visibility(rpc, mask, bits, count, grid)
+    v = torch.randn(6, 196, 8, 32, device=DEV)
+    logits = torch.randn(64, 192, device=DEV)
+    slots = ops.sca_sample(v, logits, vis, 14, 14, 8, 8)
+    assert (slots == 0).all()
+
+
+# ------------------------------------------------------------------ A5
+@pytest.mark.parametrize('name', ['small', 'dh96', 'rect'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+def test_msda_golden(name, dtype):
+    c = sub(load_golden('msda_cases.npz'), name)
+    v = cuda(c['value']).to(dtype).requires_grad_(True)
+    l = cuda(c['loc']).requires_grad_(True)
+    w = cuda(c['w']).requires_grad_(True)
+    out = ops.MultiScaleDeformableAttnFunction.apply(v, c['shape'][None], None, l, w, 64)
+    tol = TOL[dtype]
+    if dtype == torch.float16:
+        # golden computed from the fp16-rounded value so only kernel error is measured
+        v64 = v.detach().double().cpu().requires_grad_(True)
+        l64, w64 = c['loc'].double().requires_grad_(True), c['w'].double().requires_grad_(True)
+        ref = ver_ref.multi_scale_deformable_attn_pytorch(v64, c['shape'][None], l64, w64)
+        go = c['gout'].to(dtype).double()
+        gv_r, gl_r, gw_r = torch.autograd.grad(ref, (v64, l64, w64), go)
+    else:
+        ref, gv_r, gl_r, gw_r, go = c['out'], c['gvalue'], c['gloc'], c['gw'], c['gout']
+    assert rel_err(out, ref) < tol
+    out.backward(cuda(go).to(dtype))
+    assert rel_err(v.grad, gv_r) < 2 * tol
+    assert rel_err(l.grad, gl_r) < 2 * tol
+    assert rel_err(w.grad, gw_r) < 2 * tol
+
+
+@pytest.mark.parametrize('Dh', [32, 64, 96, 128])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+def test_msda_random_vs_oracle(Dh, dtype):
+    g = torch.Generator().manual_seed(Dh)
+    Bv, Nq, NH, NP = 5, 777, 8, 8
+    v = (torch.randn(Bv, 196, NH, Dh, generator=g) * 0.5).to(dtype)
+    loc = torch.rand(Bv, Nq, NH, 1, NP, 2, generator=g) * 1.4 - 0.2
+    w = torch.rand(Bv, Nq, NH, 1, NP, generator=g).softmax(-1)
+    ref = ver_ref.multi_scale_deformable_attn_pytorch(v.double(), torch.tensor([[14, 14]]), loc.double(),
+                                                      w.double())
+    out = ops.ms_deform_attn_forward(cuda(v), [[14, 14]], None, cuda(loc), cuda(w))
+    assert rel_err(out, ref) < TOL[dtype]
+
+
+# ------------------------------------------------------------------ A3 / A4 / A6 / A7 golden
+def build_sca(C, ncam):
+    return V.registry.build_attention(dict(
+        type='SpatialCrossAttention', embed_dims=C, num_cams=ncam, pc_range=PC, dropout=0.1,
+        batch_first=True,
+        deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C, num_points=8,
+                                  num_levels=1))).to(DEV).eval()
+
+
+@pytest.mark.parametrize('tag', ['c6', 'c18'])
+def test_sca_module_golden(tag):
+    g = load_golden('sca.npz')
+    c, sd = sub(g, tag), sub(g, tag + '.sd')
+    grid = tuple(c['grid'].tolist())
+    ncam = c['lidar2img'].shape[1]
+    m = build_sca(c['query'].shape[-1], ncam)
+    m.load_state_dict(sd)
+    rpc, mask, bits, count = ops.point_sampling(cuda(c['lidar2img']), cuda(c['originshift']), PC, *grid)
+    with torch.no_grad():
+        # plain reference signature (visibility derived from bev_mask inside the module)
+        y = m(cuda(c['query']), cuda(c['value']), cuda(c['value']), reference_points_cam=rpc,
+              bev_mask=mask, spatial_shapes=torch.tensor([[14, 14]]), level_start_index=torch.tensor([0]))
+    assert rel_err(y, c['out']) < 1e-5
+
+
+def test_encoder_golden():
+    g = load_golden('encoder_6cam_c256.npz')
+    c = {k: torch.from_numpy(v) for k, v in g.items() if not k.startswith('sd.')}
+    sd = sub(g, 'sd')
+    grid = tuple(c['grid'].tolist())
+    cfg = V.vocc_head_cfg(*grid, num_cams=6, embed_dims=256, num_layers=2, ffn_dims=256)
+    enc = V.registry.build_transformer_layer_sequence(cfg['transformer']['encoder']).to(DEV).eval()
+    enc.load_state_dict(sd)
+    with torch.no_grad():
+        y = enc(cuda(c['bev_query']), cuda(c['value']), cuda(c['value']), bev_z=grid[0], bev_h=grid[1],
+                bev_w=grid[2], bev_pos=None, spatial_shapes=[[14, 14]], level_start_index=[0],
+                img_metas=[dict(lidar2img=c['lidar2img'][0], originshift=c['originshift'][0])])
+    assert rel_err(y, c['out']) < 1e-5
+
+
+def test_head_golden_and_decode_bit_exact():
+    g = load_golden('head.npz')
+    for tag in ('pervoxel', 'column'):
+        c, sd = sub(g, tag), sub(g, tag + '.sd')
+        grid = tuple(c['grid'].tolist())
+        osz = per_voxel_occupancy_size(*grid) if tag == 'pervoxel' else [2.0, 2.0, 0.5]
+        cfg = V.vocc_head_cfg(*grid, num_cams=6, embed_dims=32, only_occ=True, refine_occ=False,
+                              occupancy_size=osz, occ_dims=16, num_layers=1)
+        head = V.build_head(cfg).to(DEV).eval()
+        head.load_state_dict(sd, strict=False)
+        with torch.no_grad():
+            y = head._occupancy_tail(cuda(c['bev_embed']), 1)
+            pos = head.positional_encoding(torch.zeros(1, *grid, device=DEV))
+        assert rel_err(y, c['occupancy_preds']) < 1e-5
+        assert torch.equal(pos.cpu(), c['pos'])
+        dec = head.get_occupancy_prediction(dict(occupancy_preds=cuda(c['decode_logits']), flow_preds=None))
+        assert torch.equal(dec['occupancy_preds'].cpu(), c['decode']), 'decode index tensor must be bit-exact'
+
+
+# ------------------------------------------------------------------ full lift+encode vs oracle
+def make_head(grid, ncam, C=768, seed=0, **kw):
+    torch.manual_seed(seed)
+    cfg = V.vocc_head_cfg(*grid, num_cams=ncam, embed_dims=C, only_occ=True, refine_occ=False,
+                          occupancy_size=per_voxel_occupancy_size(*grid), **kw)
+    head = V.build_head(cfg)
+    head.init_weights()
+    g = torch.Generator().manual_seed(seed + 100)
+    for n, p in head.named_parameters():       # query-dependent offsets / weights
+        if n.endswith('sampling_offsets.weight') or n.endswith('attention_weights.weight'):
+            with torch.no_grad():
+                p.add_(torch.randn(p.shape, generator=g) * 0.02)
+    return head.eval()
+
+
+def oracle_forward(head, feats, l2i, sh, grid):
+    sd = {k: v.detach().cpu().float() for k, v in head.state_dict().items()}
+    bev = ver_ref.get_voxel_features(sd, 'transformer.', feats, sd['voxel_embedding.weight'], *grid, PC,
+                                     l2i, sh)
+    occ = ver_ref.occ_head(sd, '', bev, *grid, head.occ_xdim, head.occ_ydim, head.occ_zdim,
+                           occ_dims=head.occ_dims, refine_occ=False, only_occ=True)
+    return bev, occ
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('ncam,B,grid', [(18, 2, (8, 20, 20)), (6, 1, (4, 15, 15))])
+def test_lift_encode_head_vs_oracle(dtype, ncam, B, grid):
+    head = make_head(grid, ncam)
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=9)
+    feats = torch.from_numpy(synth.make_features(B, ncam, seed=10))
+    l2i, sh = torch.from_numpy(l2i), torch.from_numpy(sh)
+    with torch.no_grad():
+        bev_ref, occ_ref = oracle_forward(head, feats, l2i, sh, grid)
+    head = head.to(DEV)
+    V.set_compute_dtype(head, dtype)
+    with torch.no_grad():
+        outs = head(cuda(feats), None, lidar2img=cuda(l2i), originshift=cuda(sh))
+    # fp16 storage through 3 layers of GEMMs: tolerance on the encoder output is the fp16 one
+    assert rel_err(outs['bev_embed'], bev_ref) < (1e-5 if dtype == torch.float32 else 4e-3)
+    assert rel_err(outs['occupancy_preds'], occ_ref) < (2e-5 if dtype == torch.float32 else 4e-3)
+
+
+def test_training_gradients_vs_oracle_autograd():
+    """forward+backward through SCA (fused sampler fwd/bwd), LN, FFN, head and focal loss,
+    fp32, against torch autograd on the CPU oracle."""
+    grid, ncam, B, C = (4, 8, 8), 18, 2, 256
+    head = make_head(grid, ncam, C=C, num_layers=2, occ_dims=32)
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=19)
+    feats = torch.from_numpy(synth.make_features(B, ncam, dim=C, seed=20))
+    l2i, sh = torch.from_numpy(l2i), torch.from_numpy(sh)
+    gts = [torch.from_numpy(x) for x in synth.make_occ_gt(B, head.voxel_num, frac=0.2)]
+    # oracle
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in head.state_dict().items()}
+    bev = ver_ref.get_voxel_features(sd, 'transformer.', feats.double(), sd['voxel_embedding.weight'],
+                                     *grid, PC, l2i, sh, num_layers=2)
+    occ = ver_ref.occ_head(sd, '', bev, *grid, head.occ_xdim, head.occ_ydim, head.occ_zdim,
+                           occ_dims=32, refine_occ=False, only_occ=True)
+    loss_ref = ver_ref.occupancy_loss(occ, gts)
+    loss_ref.backward()
+    # product
+    head = head.to(DEV).train()
+    for m in head.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    outs = head(cuda(feats), None, lidar2img=cuda(l2i), originshift=cuda(sh))
+    loss = head.loss_only_occupancy(None, None, None, [cuda(t) for t in gts], None, outs)['loss_occupancy']
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+    loss.backward()
+    checked = 0
+    for n, p in head.named_parameters():
+        gref = sd[n].grad
+        if gref is None or p.grad is None:
+            continue
+        if gref.abs().max() < 1e-12:
+            assert p.grad.abs().max() < 1e-9
+            continue
+        assert rel_err(p.grad, gref) < 2e-4, n
+        checked += 1
+    assert checked >= 30
+
+
+def test_focal_loss_vs_oracle():
+    torch.manual_seed(1)
+    N = 5000
+    x = torch.randn(N, 16) * 2
+    gt = torch.from_numpy(synth.make_occ_gt(1, N, frac=0.1)[0])
+    xr = x.double().requires_grad_(True)
+    ref = ver_ref.occupancy_loss(xr[None], [gt])
+    ref.backward()
+    xc = cuda(x).requires_grad_(True)
+    loss = ops.occupancy_focal_loss(xc, cuda(gt))
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_err(xc.grad, xr.grad) < 1e-5
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_full_size_properties():
+    """BASELINE config-2/3 shape (18 views, 16x40x40): linearity of the sampler in `value`,
+    zero slots for invisible voxels, batch-permutation equivariance."""
+    grid, ncam, B = (16, 40, 40), 18, 4
+    Nq = 16 * 40 * 40
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=3)
+    l2i, sh = cuda(torch.from_numpy(l2i)), cuda(torch.from_numpy(sh))
+    rpc, mask, bits, count = ops.point_sampling(l2i, sh, PC, *grid)
+    vis = ops.Visibility(rpc, mask, bits, count, grid)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    v1 = torch.randn(B * ncam, 196, 8, 96, device=DEV, generator=g)
+    v2 = torch.randn(B * ncam, 196, 8, 96, device=DEV, generator=g)
+    logits = torch.randn(B * Nq, 192, device=DEV, generator=g)
+    logits[:, :128] *= 3.0
+    s1 = ops.sca_sample(v1, logits, vis, 14, 14, 8, 8)
+    s2 = ops.sca_sample(v2, logits, vis, 14, 14, 8, 8)
+    s12 = ops.sca_sample(2.5 * v1 + v2, logits, vis, 14, 14, 8, 8)
+    assert rel_err(s12, 2.5 * s1 + s2) < 1e-5
+    assert (s1[count == 0] == 0).all()
+    # permute the batch: outputs permute with it
+    perm = torch.tensor([2, 0, 3, 1], device=DEV)
+    rpc_p, mask_p, bits_p, count_p = ops.point_sampling(l2i[perm], sh[perm], PC, *grid)
+    vis_p = ops.Visibility(rpc_p, mask_p, bits_p, count_p, grid)
+    v1p = v1.view(B, ncam, 196, 8, 96)[perm].reshape(B * ncam, 196, 8, 96)
+    lp = logits.view(B, Nq, 192)[perm].reshape(B * Nq, 192)
+    s1p = ops.sca_sample(v1p, lp, vis_p, 14, 14, 8, 8)
+    assert torch.equal(s1p, s1[perm])
+    # fp16 storage agrees with fp32 within the fp16 tolerance
+    s1h = ops.sca_sample(v1.half(), logits, vis, 14, 14, 8, 8)
+    s1f = ops.sca_sample(v1.half().float(), logits, vis, 14, 14, 8, 8)
+    assert rel_err(s1h, s1f) < 1e-3

@@ -1,0 +1,57 @@
+"""CPU tier, build container only: re-runs the UNMODIFIED reference (imported from
+/root/reference through oracle/mmcv_shim.py) and checks that (a) the committed golden
+fixtures are what the reference produces and (b) the oracle restatement agrees with it."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmcv_shim, ver_ref
+from vln_ver_b200 import synth
+from conftest import load_golden, rel_err, sub
+
+pytestmark = pytest.mark.skipif(not mmcv_shim.reference_available(),
+                                reason='/root/reference is only present in the build container')
+PC = synth.PC_RANGE
+
+
+def test_unmodified_point_sampling_reproduces_fixture():
+    from oracle import gen_golden
+    enc_mod = mmcv_shim.import_reference('bevformer.modules.voxel_encoder')
+    g = load_golden('point_sampling_6cam.npz')
+    c = sub(g, 'g4x15x15')
+    ref_3d, rpc, mask = gen_golden.run_unmodified_point_sampling(
+        enc_mod, 4, 15, 15, c['lidar2img'][0].numpy(), c['originshift'][0].numpy())
+    assert torch.equal(rpc, c['rpc']) and torch.equal(mask, c['mask'])
+
+
+def test_unmodified_sca_18_views_matches_oracle_on_fresh_inputs():
+    sca_mod = mmcv_shim.import_reference('bevformer.modules.spatial_cross_attention')
+    torch.manual_seed(7)
+    C, ncam, grid = 64, 18, (2, 6, 6)
+    m = sca_mod.SpatialCrossAttention(
+        embed_dims=C, num_cams=ncam, pc_range=PC, dropout=0.1, batch_first=True,
+        deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C, num_points=8,
+                                  num_levels=1)).eval()
+    l2i, sh = synth.make_rig(1, ncam, grid, seed=77)
+    rpc, mask = ver_ref.point_sampling_batched(*grid, PC, torch.from_numpy(l2i), torch.from_numpy(sh))
+    q = torch.randn(1, 72, C)
+    v = torch.randn(ncam, 196, 1, C)
+    with torch.no_grad():
+        y = m(q, v, v, reference_points_cam=rpc, bev_mask=mask, spatial_shapes=torch.tensor([[14, 14]]),
+              level_start_index=torch.tensor([0]))
+        y2 = ver_ref.sca_forward(dict(m.state_dict()), '', q, v, rpc, mask, torch.tensor([[14, 14]]))
+    assert rel_err(y2, y) < 1e-6
+
+
+def test_reference_3d_sampler_at_depth_one_equals_2d_restatement():
+    vtsa = mmcv_shim.import_reference('bevformer.modules.voxel_temporal_self_attention')
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(2, 35, 4, 8, generator=g, dtype=torch.float64)
+    loc = torch.rand(2, 11, 4, 1, 6, 2, generator=g, dtype=torch.float64) * 1.4 - 0.2
+    w = torch.rand(2, 11, 4, 1, 6, generator=g, dtype=torch.float64)
+    loc3 = torch.cat([loc, torch.full_like(loc[..., :1], 0.5)], -1)
+    a = vtsa.voxel_multi_scale_deformable_attn_pytorch(v, [(1, 5, 7)], loc3, w)
+    b = ver_ref.multi_scale_deformable_attn_pytorch(v, torch.tensor([[5, 7]]), loc, w)
+    assert (a - b).abs().max().item() < 1e-13

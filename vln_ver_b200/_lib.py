@@ -1,0 +1,69 @@
+"""ctypes binding of libver_b200.so (the C ABI declared in include/ver_b200.h).
+
+The library is the product: there is NO fallback.  If it cannot be loaded the
+import raises, and every op raises if it is handed a non-CUDA tensor.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libver_b200.so')
+
+VER_F32, VER_F16 = 0, 1
+ABI_VERSION = 1
+
+
+class VerError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        # built in-tree by `python -m vln_ver_b200.build` / __graft_entry__.build()
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise VerError(
+                f'libver_b200.so is missing and could not be built ({e}); '
+                'run `python -m vln_ver_b200.build`') from e
+    lib = ctypes.CDLL(LIB_PATH)
+    P = c_void_p
+    sig = {
+        'ver_abi_version': (c_int, []),
+        'ver_last_error': (c_char_p, []),
+        'ver_launch_count': (c_int64, []),
+        'ver_point_sampling_f32': (c_int, [P, P, ctypes.POINTER(c_double), c_int, c_int, c_int, c_int,
+                                           c_int, c_float, c_float, P, P, P, P, P]),
+        'ver_visible_index': (c_int, [P, c_int, c_int, c_int, P, P, P]),
+        'ver_msda_forward': (c_int, [c_int, P, ctypes.POINTER(c_int32), c_int, P, P, P, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, P]),
+        'ver_msda_backward': (c_int, [c_int, P, ctypes.POINTER(c_int32), c_int, P, P, P, P, P, P, c_int,
+                                      c_int, c_int, c_int, c_int, c_int, P]),
+        'ver_sca_forward': (c_int, [c_int, P, P, c_int, P, P, P] + [c_int] * 10 + [P]),
+        'ver_sca_backward': (c_int, [c_int, P, P, c_int, P, P, P, P, P, P, P] + [c_int] * 10 + [P]),
+        'ver_feat_embed': (c_int, [c_int, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+        'ver_add_layernorm': (c_int, [c_int, P, P, P, P, P, c_int64, c_int, c_float, P]),
+        'ver_focal_loss': (c_int, [P, P, c_int, P, P, P, P, c_int64, c_int, c_float, c_float, P]),
+        'ver_occupancy_decode': (c_int, [P, c_int64, c_int, c_float, P, P, P, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ver_abi_version() != ABI_VERSION:
+        raise VerError(f'libver_b200.so ABI {lib.ver_abi_version()} != expected {ABI_VERSION}')
+    return lib, tuple(sig)
+
+
+lib, EXPORTED = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise VerError(f'libver_b200 error {rc}: {lib.ver_last_error().decode()}')
+
+
+def launch_count():
+    return int(lib.ver_launch_count())

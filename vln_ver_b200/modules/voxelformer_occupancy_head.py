@@ -1,0 +1,216 @@
+"""VoxelFormerOccupancyHead -- occupancy part of
+projects/mmdet3d_plugin/bevformer/dense_heads/voxelformer_occupancy_head.py (HEAD):
+query embedding -> VoxelPerceptionTransformer -> [up_sample] -> occ_proj -> occ_branches
+(HEAD:300-308, :323-352, :551-580), sigmoid focal occupancy loss (HEAD:1386-1444) and the
+sparse decode (HEAD:1505-1524).  The DETR-style box / layout branches are a different task
+("OUT OF SCOPE") and are not built.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..registry import (HAVE_MMCV, HEADS, LOSSES, BaseModule, bias_init_with_prob,
+                        build_loss, build_positional_encoding, build_transformer)
+from .precision import PrecisionMixin
+from .voxel_encoder import apply_layernorm
+
+
+class FocalLoss(nn.Module):
+    """mmdet FocalLoss(use_sigmoid=True) surface (vocc.py:190-195) on ver_focal_loss."""
+
+    def __init__(self, use_sigmoid=True, gamma=2.0, alpha=0.25, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        assert use_sigmoid is True, 'Only sigmoid focal loss supported now.'
+        self.use_sigmoid, self.gamma, self.alpha = use_sigmoid, gamma, alpha
+        self.reduction, self.loss_weight = reduction, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        """pred (N, C) logits, target (N,) class ids in [0, C] (C = background)."""
+        assert weight is None, 'per-sample weights are not used on the occupancy path'
+        reduction = reduction_override if reduction_override else self.reduction
+        assert reduction == 'mean'
+        loss_sum, _ = ops._FocalFunction.apply(pred, target, self.gamma, self.alpha)
+        denom = avg_factor if avg_factor is not None else pred.numel()
+        return self.loss_weight * loss_sum[0] / denom
+
+
+class _CfgHolder(nn.Module):
+    """Stands in for detection-only losses so vocc.py's loss_cls / loss_bbox / loss_iou dicts build."""
+
+    def __init__(self, **cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.use_sigmoid = cfg.get('use_sigmoid', False)
+        self.loss_weight = cfg.get('loss_weight', 1.0)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError('detection losses are outside the lift+encode hot path')
+
+
+if not HAVE_MMCV or LOSSES.get('FocalLoss') is None:
+    LOSSES.register_module(name='FocalLoss', module=FocalLoss)
+    for _n in ('L1Loss', 'GIoULoss'):
+        LOSSES.register_module(name=_n, module=type(_n, (_CfgHolder,), {}))
+
+
+@HEADS.register_module()
+class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
+    def __init__(self, *args, with_box_refine=True, as_two_stage=False, transformer=None,
+                 bbox_coder=None, num_cls_fcs=2, code_weights=None, bev_h=120, bev_w=120, bev_z=4,
+                 num_layout_query=10, getbev=None, occupancy_size=[0.1, 0.1, 0.1],
+                 point_cloud_range=[-6.0, -6.0, -1.5, 6.0, 6.0, 2.0], loss_layout=None,
+                 loss_occupancy=None, loss_flow=None, flow_gt_dimension=2, occ_dims=16, det_dims=None,
+                 num_occ_fcs=2, occupancy_classes=1, only_occ=False, only_det=False, add_layout=False,
+                 with_occupancy_flow=False, with_color_render=False, occ_weights=None,
+                 flow_weights=None, occ_loss_type='focal_loss', occ_head_type='mlp',
+                 occ_head_network=None, refine_occ=False,
+                 # DETRHead kwargs that vocc.py passes (HEAD:87-195)
+                 num_classes=17, in_channels=768, num_query=100, num_reg_fcs=2,
+                 sync_cls_avg_factor=False, positional_encoding=None, loss_cls=None, loss_bbox=None,
+                 loss_iou=None, train_cfg=None, test_cfg=None, init_cfg=None, **kwargs):
+        super().__init__(init_cfg)
+        self.bev_h, self.bev_w, self.bev_z = bev_h, bev_w, bev_z
+        self.fp16_enabled = False
+        self.only_occ, self.only_det, self.add_layout = only_occ, only_det, add_layout
+        self.occ_loss_type, self.occ_head_type = occ_loss_type, occ_head_type
+        self.refine_occ = refine_occ
+        self.getbev = getbev
+        self.with_box_refine, self.as_two_stage = with_box_refine, as_two_stage
+        self.num_classes, self.in_channels, self.num_query = num_classes, in_channels, num_query
+        self.occ_weights = occ_weights
+        self.pc_range = (bbox_coder or {}).get('pc_range', point_cloud_range)
+        self.real_w = self.pc_range[3] - self.pc_range[0]
+        self.real_h = self.pc_range[4] - self.pc_range[1]
+        self.real_z = self.pc_range[5] - self.pc_range[2]
+        self.occupancy_size = occupancy_size
+        self.point_cloud_range = point_cloud_range
+        # HEAD:144-146 -- Python float division then int() truncation
+        self.occ_xdim = int((point_cloud_range[3] - point_cloud_range[0]) / occupancy_size[0])
+        self.occ_ydim = int((point_cloud_range[4] - point_cloud_range[1]) / occupancy_size[1])
+        self.occ_zdim = int((point_cloud_range[5] - point_cloud_range[2]) / occupancy_size[2])
+        self.occ_dims, self.num_occ_fcs = occ_dims, num_occ_fcs
+        self.occupancy_classes = occupancy_classes
+        self.voxel_num = self.occ_xdim * self.occ_ydim * self.occ_zdim
+        self.bev_num = self.bev_h * self.bev_w * self.bev_z
+        transformer = copy.deepcopy(dict(transformer))
+        if self.only_occ:
+            transformer['decoder'] = None                                     # HEAD:160-161
+        self.positional_encoding = build_positional_encoding(positional_encoding)
+        self.transformer = build_transformer(transformer)
+        self.embed_dims = self.transformer.embed_dims
+        assert positional_encoding['num_feats'] * 2 == self.embed_dims
+        self.loss_occupancy = build_loss(loss_occupancy)
+        self.loss_cls = build_loss(loss_cls) if (loss_cls and not only_occ) else None
+        self._init_layers()
+
+    def _init_layers(self):
+        """voxel_embedding, occ_proj, occ_branches, up_sample (HEAD:226-258)."""
+        self.voxel_embedding = nn.Embedding(self.bev_num, self.embed_dims)
+        if self.bev_z == self.occ_zdim:
+            self.occ_proj = nn.Linear(self.embed_dims, self.occ_dims)
+        else:
+            self.occ_proj = nn.Linear(self.bev_z * self.embed_dims, self.occ_dims * self.occ_zdim)
+        occ_branch = []
+        for _ in range(self.num_occ_fcs):
+            occ_branch += [nn.Linear(self.occ_dims, self.occ_dims), nn.LayerNorm(self.occ_dims),
+                           nn.ReLU(inplace=True)]
+        occ_branch.append(nn.Linear(self.occ_dims, self.occupancy_classes))
+        self.occ_branches = nn.Sequential(*occ_branch)
+        if self.refine_occ:
+            # 8x lateral upsampling of the voxel volume, library conv
+            self.up_sample = nn.Sequential(*[
+                nn.ConvTranspose3d(768, 768, (3, 5, 5), stride=(1, 2, 2), padding=(2, 4, 4),
+                                   dilation=(2, 2, 2), output_padding=(0, 1, 1)) for _ in range(3)])
+
+    def init_weights(self):
+        self.transformer.init_weights()
+        self.positional_encoding.init_weights()
+        if self.loss_occupancy.use_sigmoid:
+            nn.init.constant_(self.occ_branches[-1].bias, bias_init_with_prob(0.01))
+
+    # ------------------------------------------------------------------ A10
+    def _occupancy_tail(self, bev_embed, bs):
+        """bev_embed (bs, Nq, C) -> occupancy logits (bs, occ_z*occ_y*occ_x, classes).
+        Per-sample semantics of the raw `.view`s at HEAD:334 / :558 / :564."""
+        cd = self.compute_dtype or bev_embed.dtype
+        C = self.embed_dims
+        x = bev_embed.contiguous()
+        if self.refine_occ and not self.only_occ:
+            x = x.view(bs, C, self.bev_z, self.bev_h, self.bev_w)
+            w_dtype = cd
+            for conv in self.up_sample:
+                x = nn.functional.conv_transpose3d(
+                    x.to(w_dtype), conv.weight.to(w_dtype), conv.bias.to(w_dtype), stride=conv.stride,
+                    padding=conv.padding, output_padding=conv.output_padding, dilation=conv.dilation)
+            x = x.contiguous().view(bs, self.bev_z, self.occ_xdim, self.occ_ydim, C)
+            lat = (self.occ_xdim, self.occ_ydim)
+        else:
+            x = x.view(bs, self.bev_z, self.bev_h, self.bev_w, C)
+            lat = (self.bev_h, self.bev_w)
+        if self.bev_z == self.occ_zdim:
+            occ = self._linear(x, self.occ_proj, cd)
+        else:
+            x = x.permute(0, 2, 3, 1, 4).flatten(3)
+            occ = self._linear(x, self.occ_proj, cd)
+            occ = occ.view(bs, lat[0], lat[1], self.occ_zdim, self.occ_dims).permute(0, 3, 1, 2, 4)
+        y = occ.reshape(bs, -1, self.occ_dims)
+        for layer in self.occ_branches:
+            if isinstance(layer, nn.Linear):
+                y = self._linear(y, layer, cd)
+            elif isinstance(layer, nn.LayerNorm):
+                y = apply_layernorm(layer, y)
+            else:
+                y = layer(y)
+        return y.float()
+
+    def forward(self, mlvl_feats, img_metas, prev_bev=None, only_bev=False, **cam):
+        """mlvl_feats (Ncam, bs, S, C).  `cam` may carry device tensors lidar2img (bs, Ncam, 4, 4)
+        and originshift (bs, 3) instead of img_metas lookups.  Returns the reference's dict
+        (HEAD:357-367 / :615-625); detection entries are None."""
+        num_cam, bs, _, _ = mlvl_feats.shape
+        voxel_queries = self.voxel_embedding.weight
+        needs_pos = any('self_attn' in l.operation_order for l in self.transformer.encoder.layers)
+        voxel_pos = None
+        if needs_pos:       # A9: only a self-attention layer ever reads it
+            voxel_pos = self.positional_encoding(
+                torch.zeros((bs, self.bev_z, self.bev_h, self.bev_w), device=voxel_queries.device))
+        bev_embed = self.transformer.get_voxel_features(
+            mlvl_feats, voxel_queries, self.bev_z, self.bev_h, self.bev_w,
+            grid_length=(self.real_h / self.bev_h, self.real_w / self.bev_w), bev_pos=voxel_pos,
+            img_metas=img_metas, prev_bev=prev_bev, **cam)
+        if only_bev:
+            return bev_embed
+        outs = {'bev_embed': bev_embed if self.only_occ else bev_embed.permute(1, 0, 2),
+                'all_cls_scores': None, 'all_bbox_preds': None, 'all_layout_preds': None,
+                'occupancy_preds': self._occupancy_tail(bev_embed, bs), 'flow_preds': None,
+                'enc_cls_scores': None, 'enc_bbox_preds': None, 'enc_occupancy_preds': None}
+        return outs
+
+    # ------------------------------------------------------------------ A11
+    def loss_only_occupancy(self, gt_bboxes_list, gt_labels_list, point_coords, occ_gts, flow_gts,
+                            preds_dicts, gt_bboxes_ignore=None, img_metas=None):
+        """occ_gts: per panorama an (n, 2) int64 tensor (flat index, class) -- the reference's
+        `occ_gts[0][0]` (HEAD:1408) generalised to a batch; the batch loss is the mean of the
+        per-panorama losses."""
+        preds = preds_dicts['occupancy_preds']
+        losses = []
+        for b in range(preds.shape[0]):
+            gt = occ_gts[b]
+            gt = gt[0] if isinstance(gt, (list, tuple)) else gt
+            losses.append(ops.occupancy_focal_loss(
+                preds[b].reshape(-1, self.occupancy_classes), gt.to(preds.device),
+                gamma=self.loss_occupancy.gamma, alpha=self.loss_occupancy.alpha,
+                loss_weight=self.loss_occupancy.loss_weight))
+        loss = torch.stack(losses).mean()
+        return {'loss_occupancy': loss, 'loss_flow': torch.zeros_like(loss)}
+
+    # ------------------------------------------------------------------ A12
+    def get_occupancy_prediction(self, occ_results, occ_threshold=0.25):
+        if self.occ_loss_type != 'focal_loss':
+            raise NotImplementedError(self.occ_loss_type)
+        occ_results['occupancy_preds'] = ops.occupancy_decode(
+            occ_results['occupancy_preds'].reshape(-1, self.occupancy_classes), occ_threshold)
+        occ_results['flow_preds'] = None
+        return occ_results

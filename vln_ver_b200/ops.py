@@ -1,0 +1,316 @@
+"""torch-facing wrappers of the C ABI (include/ver_b200.h).
+
+torch is plumbing here: device memory, the current stream and autograd graph
+bookkeeping.  Every function requires CUDA tensors and raises otherwise -- there is
+no CPU or eager fallback (the CPU restatement lives in oracle/ and is test-only).
+"""
+import ctypes
+from ctypes import c_double, c_int32, c_void_p
+
+import torch
+from torch.autograd.function import Function, once_differentiable
+
+from ._lib import VER_F16, VER_F32, VerError, check, lib
+
+IMG_W, IMG_H = 1280.0, 1024.0     # hard-coded in the reference, M/voxel_encoder.py:179-180
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise VerError('vln_ver_b200 ops need CUDA tensors (no CPU fallback); got a '
+                           f'{t.device} tensor')
+
+
+def _code(dtype):
+    if dtype == torch.float32:
+        return VER_F32
+    if dtype == torch.float16:
+        return VER_F16
+    raise VerError(f'unsupported storage dtype {dtype} (float32 / float16 only)')
+
+
+def _c(t, dtype=None):
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------ A1 + A2, K8
+def point_sampling(lidar2img, originshift, pc_range, bev_z, bev_h, bev_w, img_w=IMG_W, img_h=IMG_H):
+    """Batched VoxelFormerEncoder.get_reference_points('3d') + point_sampling math
+    (M/voxel_encoder.py:53-83, :136-195).  lidar2img (B, Ncam, 4, 4), originshift (B, 3).
+    Returns reference_points_cam (Ncam, B, Nq, 1, 2) fp32, bev_mask (Ncam, B, Nq, 1) bool,
+    vis_bits (B, Nq) int32 (bit c = camera c sees the voxel; None if Ncam > 32), count (B, Nq) int32."""
+    _need_cuda(lidar2img, originshift)
+    lidar2img = _c(lidar2img, torch.float32)
+    originshift = _c(originshift, torch.float32)
+    B, Ncam = lidar2img.shape[:2]
+    assert lidar2img.shape[2:] == (4, 4) and originshift.shape == (B, 3)
+    Nq = bev_z * bev_h * bev_w
+    dev = lidar2img.device
+    rpc = torch.empty((Ncam, B, Nq, 1, 2), dtype=torch.float32, device=dev)
+    mask = torch.empty((Ncam, B, Nq, 1), dtype=torch.uint8, device=dev)
+    bits = torch.empty((B, Nq), dtype=torch.int32, device=dev) if Ncam <= 32 else None
+    count = torch.empty((B, Nq), dtype=torch.int32, device=dev)
+    pc = (c_double * 6)(*[float(x) for x in pc_range])
+    check(lib.ver_point_sampling_f32(_ptr(lidar2img), _ptr(originshift), pc, B, Ncam, bev_z, bev_h,
+                                     bev_w, float(img_w), float(img_h), _ptr(rpc), _ptr(mask),
+                                     _ptr(bits), _ptr(count), _stream()))
+    return rpc, mask.view(torch.bool), bits, count
+
+
+def visible_index(bev_mask):
+    """Device-side replacement of the per-camera nonzero() of
+    M/spatial_cross_attention.py:138-142.  bev_mask (Ncam, B, Nq[, 1]) bool ->
+    counts (B, Ncam) int32, index (B, Ncam, Nq) int32 ascending, -1 padded."""
+    _need_cuda(bev_mask)
+    if bev_mask.dim() == 4:
+        assert bev_mask.shape[-1] == 1, 'D (points per voxel) is 1 on this path (SURVEY A4.1)'
+        bev_mask = bev_mask[..., 0]
+    m = _c(bev_mask.view(torch.uint8) if bev_mask.dtype == torch.bool else bev_mask.to(torch.uint8))
+    Ncam, B, Nq = m.shape
+    counts = torch.empty((B, Ncam), dtype=torch.int32, device=m.device)
+    index = torch.empty((B, Ncam, Nq), dtype=torch.int32, device=m.device)
+    check(lib.ver_visible_index(_ptr(m), B, Ncam, Nq, _ptr(counts), _ptr(index), _stream()))
+    return counts, index
+
+
+# ------------------------------------------------------------------ A5 (operator boundary)
+def _shapes_arg(spatial_shapes):
+    if isinstance(spatial_shapes, torch.Tensor):
+        spatial_shapes = spatial_shapes.tolist()          # one D2H copy if it lives on the GPU
+    flat = [int(v) for hw in spatial_shapes for v in hw]
+    return (c_int32 * len(flat))(*flat), len(flat) // 2
+
+
+def ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                           sampling_locations, attention_weights, im2col_step=64):
+    """Drop-in for mmcv._ext.ms_deform_attn_forward
+    (M/multi_scale_deformable_attn_function.py:118-124).  value (Bv, S, NH, Dh) fp32|fp16;
+    sampling_locations (Bv, Nq, NH, NL, NP, 2); attention_weights (Bv, Nq, NH, NL, NP).
+    `value_level_start_index` and `im2col_step` are accepted for signature parity
+    (level starts are recomputed from the shapes; there is no im2col batching)."""
+    _need_cuda(value, sampling_locations, attention_weights)
+    value = _c(value)
+    loc = _c(sampling_locations, torch.float32)
+    w = _c(attention_weights, torch.float32)
+    Bv, S, NH, Dh = value.shape
+    _, Nq, _, NL, NP, _ = loc.shape
+    shapes, nl = _shapes_arg(value_spatial_shapes)
+    assert nl == NL
+    out = torch.empty((Bv, Nq, NH * Dh), dtype=value.dtype, device=value.device)
+    check(lib.ver_msda_forward(_code(value.dtype), _ptr(value), shapes, NL, _ptr(loc), _ptr(w),
+                               _ptr(out), Bv, S, NH, Dh, Nq, NP, _stream()))
+    return out
+
+
+def ms_deform_attn_backward(value, value_spatial_shapes, value_level_start_index,
+                            sampling_locations, attention_weights, grad_output, grad_value,
+                            grad_sampling_loc, grad_attn_weight, im2col_step=64):
+    """Drop-in for mmcv._ext.ms_deform_attn_backward (:150-160): fills the three
+    caller-provided buffers (fp32)."""
+    _need_cuda(value, sampling_locations, attention_weights, grad_output, grad_value)
+    value = _c(value)
+    loc = _c(sampling_locations, torch.float32)
+    w = _c(attention_weights, torch.float32)
+    go = _c(grad_output, value.dtype)
+    Bv, S, NH, Dh = value.shape
+    _, Nq, _, NL, NP, _ = loc.shape
+    shapes, _ = _shapes_arg(value_spatial_shapes)
+    for g in (grad_value, grad_sampling_loc, grad_attn_weight):
+        assert g.is_contiguous() and g.dtype == torch.float32
+    check(lib.ver_msda_backward(_code(value.dtype), _ptr(value), shapes, NL, _ptr(loc), _ptr(w),
+                                _ptr(go), _ptr(grad_value), _ptr(grad_sampling_loc),
+                                _ptr(grad_attn_weight), Bv, S, NH, Dh, Nq, NP, _stream()))
+
+
+class MultiScaleDeformableAttnFunction(Function):
+    """Mirror of MultiScaleDeformableAttnFunction_fp32
+    (M/multi_scale_deformable_attn_function.py:90-163): same positional signature,
+    same saved tensors, same gradient tuple."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index,
+                sampling_locations, attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.shapes = value_spatial_shapes.tolist() if isinstance(value_spatial_shapes, torch.Tensor) \
+            else [list(x) for x in value_spatial_shapes]
+        out = ms_deform_attn_forward(value, ctx.shapes, value_level_start_index,
+                                     sampling_locations, attention_weights, im2col_step)
+        ctx.save_for_backward(value, sampling_locations, attention_weights)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, sampling_locations, attention_weights = ctx.saved_tensors
+        grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+        grad_sampling_loc = torch.empty(sampling_locations.shape, dtype=torch.float32,
+                                        device=value.device)
+        grad_attn_weight = torch.empty(attention_weights.shape, dtype=torch.float32,
+                                       device=value.device)
+        ms_deform_attn_backward(value, ctx.shapes, None, sampling_locations, attention_weights,
+                                grad_output.contiguous(), grad_value, grad_sampling_loc,
+                                grad_attn_weight, ctx.im2col_step)
+        return (grad_value.to(value.dtype), None, None,
+                grad_sampling_loc.to(sampling_locations.dtype),
+                grad_attn_weight.to(attention_weights.dtype), None)
+
+
+# aliases under the reference's names (spatial_cross_attention.py:24-25)
+MultiScaleDeformableAttnFunction_fp32 = MultiScaleDeformableAttnFunction
+MultiScaleDeformableAttnFunction_fp16 = MultiScaleDeformableAttnFunction
+
+
+# ------------------------------------------------------------------ fused SCA sampler
+class Visibility:
+    """Per-forward camera geometry products shared by the three encoder layers."""
+
+    def __init__(self, rpc, mask, bits, count, grid):
+        self.rpc, self.mask, self.bits, self.count, self.grid = rpc, mask, bits, count, grid
+        self._index = None
+
+    @property
+    def index(self):
+        if self._index is None:
+            self._index = visible_index(self.mask)
+        return self._index
+
+
+class SCASampleFunction(Function):
+    """slots = fused sampler(value, logits) -- see ver_sca_forward in include/ver_b200.h."""
+
+    @staticmethod
+    def forward(ctx, value, logits, vis, Sh, Sw, NH, NP):
+        _need_cuda(value, logits)
+        value = _c(value)
+        logits = _c(logits, torch.float32)
+        Bv, S, C = value.shape[0], value.shape[1], value.shape[2:].numel()
+        Z, H, W = vis.grid
+        Ncam, B = vis.rpc.shape[:2]
+        assert Bv == B * Ncam and S == Sh * Sw
+        Dh = C // NH
+        Nq = Z * H * W
+        assert logits.shape[0] == B * Nq
+        if vis.bits is None:
+            raise VerError('fused SCA needs Ncam <= 32')
+        slots = torch.empty((B, Nq, C), dtype=value.dtype, device=value.device)
+        check(lib.ver_sca_forward(_code(value.dtype), _ptr(value), _ptr(logits), logits.shape[1],
+                                  _ptr(vis.rpc), _ptr(vis.bits), _ptr(slots), B, Ncam, Z, H, W, Sh, Sw,
+                                  NH, Dh, NP, _stream()))
+        ctx.save_for_backward(value, logits)
+        ctx.vis, ctx.dims = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP)
+        return slots
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_slots):
+        value, logits = ctx.saved_tensors
+        vis = ctx.vis
+        B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP = ctx.dims
+        counts, index = vis.index
+        gs = _c(grad_slots, value.dtype)
+        gvalue = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+        glogits = torch.empty(logits.shape, dtype=torch.float32, device=value.device)
+        if logits.shape[1] > NH * NP * 3:
+            glogits[:, NH * NP * 3:].zero_()
+        check(lib.ver_sca_backward(_code(value.dtype), _ptr(value), _ptr(logits), logits.shape[1],
+                                   _ptr(vis.rpc), _ptr(vis.bits), _ptr(counts), _ptr(index), _ptr(gs),
+                                   _ptr(gvalue), _ptr(glogits), B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP,
+                                   _stream()))
+        return gvalue.to(value.dtype), glogits, None, None, None, None, None
+
+
+def sca_sample(value, logits, vis, Sh, Sw, NH, NP):
+    return SCASampleFunction.apply(value, logits, vis, Sh, Sw, NH, NP)
+
+
+# ------------------------------------------------------------------ A8 prologue, A6 epilogue
+def feat_embed(feats, cams_embeds, level_embed, dtype=torch.float32):
+    """(Ncam, B, S, C) fp32 + cams_embeds[cam] + level_embeds[0] -> (B*Ncam, S, C) `dtype`
+    (M/voxel_transformer.py:146-168 + M/spatial_cross_attention.py:158-161).  No autograd:
+    the embeddings' gradients are taken by the autograd wrapper in modules/."""
+    _need_cuda(feats, level_embed)
+    feats = _c(feats, torch.float32)
+    Ncam, B, S, C = feats.shape
+    out = torch.empty((B * Ncam, S, C), dtype=dtype, device=feats.device)
+    ce = _c(cams_embeds.detach(), torch.float32) if cams_embeds is not None else None
+    le = _c(level_embed.detach(), torch.float32)
+    check(lib.ver_feat_embed(_code(dtype), _ptr(feats), _ptr(ce), _ptr(le), _ptr(out), Ncam, B, S, C,
+                             _stream()))
+    return out
+
+
+def add_layernorm(x, residual, gamma, beta, eps=1e-5):
+    """y = LayerNorm(x + residual) (inference; no autograd)."""
+    _need_cuda(x, gamma, beta)
+    x = _c(x)
+    r = _c(residual, x.dtype) if residual is not None else None
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    check(lib.ver_add_layernorm(_code(x.dtype), _ptr(x), _ptr(r), _ptr(_c(gamma.detach(), torch.float32)),
+                                _ptr(_c(beta.detach(), torch.float32)), _ptr(y), x.numel() // C, C,
+                                float(eps), _stream()))
+    return y
+
+
+# ------------------------------------------------------------------ A11, A12
+class _FocalFunction(Function):
+    @staticmethod
+    def forward(ctx, logits, occ_gt, gamma, alpha):
+        _need_cuda(logits, occ_gt)
+        x = _c(logits, torch.float32)
+        N, Ccls = x.shape
+        if occ_gt.dim() == 1:            # dense class targets (N,), values in [0, Ccls]
+            assert occ_gt.shape[0] == N
+            gt, n_gt = None, -1
+            dense = _c(occ_gt, torch.int32)
+        else:                            # sparse (n, 2) (flat index, class)
+            gt = _c(occ_gt, torch.int64)
+            n_gt = gt.shape[0]
+            dense = torch.empty((N,), dtype=torch.int32, device=x.device)
+        loss = torch.empty((1,), dtype=torch.float32, device=x.device)
+        npos = torch.empty((1,), dtype=torch.int32, device=x.device)
+        grad = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        check(lib.ver_focal_loss(_ptr(x), _ptr(gt), n_gt, _ptr(dense), _ptr(loss), _ptr(npos),
+                                 _ptr(grad), N, Ccls, float(gamma), float(alpha), _stream()))
+        ctx.grad = grad
+        ctx.in_dtype = logits.dtype
+        ctx.mark_non_differentiable(npos)
+        return loss, npos
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gloss, _gnpos):
+        return (ctx.grad * gloss).to(ctx.in_dtype), None, None, None
+
+
+def occupancy_focal_loss(logits, occ_gt, gamma=2.0, alpha=0.25, loss_weight=1.0):
+    """HEAD:1386-1444 for one panorama: dense target from sparse (index, class) GT, sigmoid
+    focal loss summed and divided by avg_factor = #(gt < classes), nan_to_num'ed."""
+    loss_sum, npos = _FocalFunction.apply(logits, occ_gt, gamma, alpha)
+    loss = loss_weight * loss_sum[0] / npos[0].to(torch.float32)
+    return torch.nan_to_num(loss)
+
+
+def occupancy_decode(logits, threshold=0.25):
+    """get_occupancy_prediction (HEAD:1505-1524) -> (n_occ, 2) int64 (flat index, class).
+    One host sync at the end to size the result (the reference's torch.where syncs too)."""
+    _need_cuda(logits)
+    x = _c(logits.reshape(-1, logits.shape[-1]), torch.float32)
+    N, Ccls = x.shape
+    pairs = torch.empty((N, 2), dtype=torch.int64, device=x.device)
+    cnt = torch.empty((1,), dtype=torch.int32, device=x.device)
+    scratch = torch.empty(((N + 1023) // 1024 + 1,), dtype=torch.int32, device=x.device)
+    check(lib.ver_occupancy_decode(_ptr(x), N, Ccls, float(threshold), _ptr(pairs), _ptr(cnt),
+                                   _ptr(scratch), _stream()))
+    return pairs[:int(cnt.item())]
