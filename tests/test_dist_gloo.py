@@ -1,0 +1,79 @@
+"""CPU tier, world_size 2 over gloo: the data-parallel contract of SURVEY.md 8(e) -- panoramas
+shard across ranks, gradients are averaged, and the result equals the single-process gradient of
+the batch-mean loss.  The model on each rank is the CPU oracle restatement (the sm_100a modules
+have no CPU path by design)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vln_ver_b200 import dist_utils, synth
+from vln_ver_b200.config import per_voxel_occupancy_size
+
+GRID, NCAM, C, B = (2, 4, 4), 6, 64, 4
+
+
+def _setup():
+    import vln_ver_b200 as V
+    torch.manual_seed(0)
+    cfg = V.vocc_head_cfg(*GRID, num_cams=NCAM, embed_dims=C, only_occ=True, refine_occ=False,
+                          occupancy_size=per_voxel_occupancy_size(*GRID), num_layers=1, occ_dims=16)
+    head = V.build_head(cfg)
+    head.init_weights()
+    l2i, sh = synth.make_rig(B, NCAM, GRID, seed=4)
+    feats = torch.from_numpy(synth.make_features(B, NCAM, dim=C, seed=5))
+    gts = [torch.from_numpy(x) for x in synth.make_occ_gt(B, head.voxel_num, frac=0.3)]
+    return head, torch.from_numpy(l2i), torch.from_numpy(sh), feats, gts
+
+
+def _loss(sd, head, feats, l2i, sh, gts):
+    from oracle import ver_ref
+    bev = ver_ref.get_voxel_features(sd, 'transformer.', feats, sd['voxel_embedding.weight'], *GRID,
+                                     synth.PC_RANGE, l2i, sh, num_layers=1)
+    occ = ver_ref.occ_head(sd, '', bev, *GRID, head.occ_xdim, head.occ_ydim, head.occ_zdim, occ_dims=16,
+                           refine_occ=False, only_occ=True)
+    return ver_ref.occupancy_loss(occ, gts)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    head, l2i, sh, feats, gts = _setup()
+    lo, hi = dist_utils.shard_range(B, rank, world)
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in head.state_dict().items()}
+    loss = _loss(sd, head, feats[:, lo:hi].double(), l2i[lo:hi], sh[lo:hi], gts[lo:hi])
+    loss.backward()
+    names = [k for k, v in sd.items() if v.grad is not None]
+    dist_utils.allreduce_mean_([sd[k].grad for k in names])
+    ms = dist_utils.max_over_ranks(10.0 + rank)
+    if rank == 0:
+        torch.save({'grads': {k: sd[k].grad for k in names}, 'ms': ms}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 8, 64):
+        for world in (1, 2, 3, 8):
+            spans = [dist_utils.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gradient_mean_equals_full_batch(tmp_path):
+    out = str(tmp_path / 'r0.pt')
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got['ms'] == 11.0                       # max over ranks
+    head, l2i, sh, feats, gts = _setup()
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in head.state_dict().items()}
+    _loss(sd, head, feats.double(), l2i, sh, gts).backward()
+    for k, g in got['grads'].items():
+        ref = sd[k].grad
+        assert torch.allclose(g, ref, rtol=1e-9, atol=1e-12), k

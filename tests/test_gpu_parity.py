@@ -101,7 +101,14 @@ def test_msda_golden(name, dtype):
     assert rel_err(out, ref) < tol
     out.backward(cuda(go).to(dtype))
     assert rel_err(v.grad, gv_r) < 2 * tol
-    assert rel_err(l.grad, gl_r) < 2 * tol
+    # d out / d loc is discontinuous where a location sits exactly on a pixel centre or on the
+    # zero-padding border (the fixture plants such points at [0, 0:2, 0, 0, :]): which one-sided
+    # derivative comes out depends on the last-bit rounding of loc*size-0.5, in the reference too
+    # (grid_sample vs mmcv's CUDA op).  Forward values and the other gradients are continuous there.
+    lg, lr = l.grad.clone().cpu().double(), gl_r.clone().double()
+    lg[0, 0:2, 0, 0] = 0
+    lr[0, 0:2, 0, 0] = 0
+    assert rel_err(lg, lr) < 2 * tol
     assert rel_err(w.grad, gw_r) < 2 * tol
 
 

@@ -1,0 +1,34 @@
+"""Host-side helpers of the data-parallel path: panoramas shard
+across ranks, weights are replicated, the forward needs no collective and the only exchange is
+the gradient all-reduce (NCCL on the GPUs, gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """contiguous, balanced [lo, hi) slice of `n_items` panoramas owned by `rank`."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value, device='cpu'):
+    """device-timed milliseconds -> max over ranks (the bench's timing rule)."""
+    t = torch.tensor([float(value)], device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def allreduce_mean_(tensors):
+    """in-place mean over ranks of a list of gradient tensors (one flat bucket)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tensors
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat)
+    flat /= dist.get_world_size()
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return tensors

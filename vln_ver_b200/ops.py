@@ -13,6 +13,7 @@ from torch.autograd.function import Function, once_differentiable
 from ._lib import VER_F16, VER_F32, VerError, check, lib
 
 IMG_W, IMG_H = 1280.0, 1024.0     # hard-coded in the reference, M/voxel_encoder.py:179-180
+PROFILE_EVENTS = None             # set to a list by bench.py to collect (start, end) CUDA events
 
 
 def _ptr(t):
@@ -204,9 +205,16 @@ class SCASampleFunction(Function):
         if vis.bits is None:
             raise VerError('fused SCA needs Ncam <= 32')
         slots = torch.empty((B, Nq, C), dtype=value.dtype, device=value.device)
+        prof = PROFILE_EVENTS
+        if prof is not None:          # bench.py: CUDA events on the launching stream around the kernel
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(lib.ver_sca_forward(_code(value.dtype), _ptr(value), _ptr(logits), logits.shape[1],
                                   _ptr(vis.rpc), _ptr(vis.bits), _ptr(slots), B, Ncam, Z, H, W, Sh, Sw,
                                   NH, Dh, NP, _stream()))
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1))
         ctx.save_for_backward(value, logits)
         ctx.vis, ctx.dims = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP)
         return slots
