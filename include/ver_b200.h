@@ -37,6 +37,10 @@ extern "C" {
 #define VER_F32 0
 #define VER_F16 1
 
+/* layout of per-view feature maps handed to the fused SCA entry points */
+#define VER_LAYOUT_MMCV 0       /* [Bv][S][NH][Dh]  (what mmcv's op takes) */
+#define VER_LAYOUT_HEAD_MAJOR 1 /* [Bv][NH][S][Dh]  (one contiguous map per (view, head): single bulk copy) */
+
 typedef void* ver_stream_t; /* cudaStream_t */
 
 /* ABI version of this header (bumped on any signature change). */
@@ -103,22 +107,23 @@ int ver_msda_backward(int dtype, const void* value, const int32_t* shapes_hw, in
  *   slots[b,n,:] = 1/max(count,1) * sum_{cam visible, ascending} sum_p softmax(aw)[p] *
  *                  bilinear(value[b*Ncam+cam], rpc[cam,b,n] + offs[p]/(Sw,Sh))
  * i.e. the tensor handed to output_proj (:174).  Never materialises the padded rebatch.
- *   value   [B*Ncam, Sh*Sw, NH, Dh] dtype (already value_proj'ed)
+ *   value   dtype, already value_proj'ed; value_layout VER_LAYOUT_MMCV [B*Ncam, Sh*Sw, NH, Dh] or
+ *           VER_LAYOUT_HEAD_MAJOR [B*Ncam, NH, Sh*Sw, Dh]; 16-byte aligned
  *   logits  [B*Nq, ld] fp32: columns [0, NH*NP*2) = sampling_offsets Linear output
  *           (layout (h, p, xy), :340-341), columns [NH*NP*2, NH*NP*3) = attention_weights
  *           Linear output BEFORE softmax (layout (h, p), :342-343)
  *   rpc, vis_bits from ver_point_sampling_f32          slots [B, Nq, NH*Dh] dtype (out)
  * Requires Ncam <= 32, NP == 8, Dh % 8 == 0 (else VER_ERR_UNSUPPORTED). */
-int ver_sca_forward(int dtype, const void* value, const float* logits, int ld_logits, const float* rpc,
-                    const uint32_t* vis_bits, void* slots, int B, int Ncam, int Z, int H, int W,
-                    int Sh, int Sw, int NH, int Dh, int NP, ver_stream_t stream);
+int ver_sca_forward(int dtype, const void* value, int value_layout, const float* logits, int ld_logits,
+                    const float* rpc, const uint32_t* vis_bits, void* slots, int B, int Ncam, int Z,
+                    int H, int W, int Sh, int Sw, int NH, int Dh, int NP, ver_stream_t stream);
 
 /* Backward of ver_sca_forward.
  *   grad_slots  [B, Nq, NH*Dh] dtype
- *   grad_value  [B*Ncam, Sh*Sw, NH, Dh] fp32 (overwritten)
+ *   grad_value  fp32, same layout as value (overwritten)
  *   grad_logits [B*Nq, ld] fp32, columns [0, NH*NP*3) overwritten
  *   counts/index from ver_visible_index (camera-major hit lists) */
-int ver_sca_backward(int dtype, const void* value, const float* logits, int ld_logits,
+int ver_sca_backward(int dtype, const void* value, int value_layout, const float* logits, int ld_logits,
                      const float* rpc, const uint32_t* vis_bits, const int32_t* counts,
                      const int32_t* index, const void* grad_slots, float* grad_value,
                      float* grad_logits, int B, int Ncam, int Z, int H, int W, int Sh, int Sw,

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_argument_validation_without_gpu():
     rc = _lib.lib.ver_msda_forward(0, None, None, 1, None, None, None, 1, 1, 1, 1, 1, 1, None)
     assert rc == -1 and b'null' in _lib.lib.ver_last_error()
-    rc = _lib.lib.ver_sca_forward(7, None, None, 0, None, None, None, *([1] * 10), None)
+    rc = _lib.lib.ver_sca_forward(7, None, 0, None, 0, None, None, None, *([1] * 10), None)
     assert rc == -1
     with pytest.raises(_lib.VerError):
         _lib.check(rc)

@@ -301,6 +301,9 @@ def test_full_size_properties():
     s12 = ops.sca_sample(2.5 * v1 + v2, logits, vis, 14, 14, 8, 8)
     assert rel_err(s12, 2.5 * s1 + s2) < 1e-5
     assert (s1[count == 0] == 0).all()
+    # head-major value layout (single bulk copy per map) is the same computation
+    s1hm = ops.sca_sample(v1.permute(0, 2, 1, 3).contiguous(), logits, vis, 14, 14, 8, 8, head_major=True)
+    assert torch.equal(s1hm, s1)
     # permute the batch: outputs permute with it
     perm = torch.tensor([2, 0, 3, 1], device=DEV)
     rpc_p, mask_p, bits_p, count_p = ops.point_sampling(l2i[perm], sh[perm], PC, *grid)

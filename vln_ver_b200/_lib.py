@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libver_b200.so')
 
 VER_F32, VER_F16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class VerError(RuntimeError):
@@ -19,12 +19,13 @@ class VerError(RuntimeError):
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        # built in-tree by `python -m vln_ver_b200.build` / __graft_entry__.build()
-        from . import build as _build
-        try:
-            _build.build()
-        except Exception as e:  # noqa: BLE001
+    # built in-tree by `python -m vln_ver_b200.build` / __graft_entry__.build(); build() is a no-op
+    # when the source digest matches the stamp written next to the .so
+    from . import build as _build
+    try:
+        _build.build()
+    except Exception as e:  # noqa: BLE001
+        if not os.path.exists(LIB_PATH):
             raise VerError(
                 f'libver_b200.so is missing and could not be built ({e}); '
                 'run `python -m vln_ver_b200.build`') from e
@@ -41,8 +42,8 @@ def _load():
                                      c_int, c_int, c_int, c_int, P]),
         'ver_msda_backward': (c_int, [c_int, P, ctypes.POINTER(c_int32), c_int, P, P, P, P, P, P, c_int,
                                       c_int, c_int, c_int, c_int, c_int, P]),
-        'ver_sca_forward': (c_int, [c_int, P, P, c_int, P, P, P] + [c_int] * 10 + [P]),
-        'ver_sca_backward': (c_int, [c_int, P, P, c_int, P, P, P, P, P, P, P] + [c_int] * 10 + [P]),
+        'ver_sca_forward': (c_int, [c_int, P, c_int, P, c_int, P, P, P] + [c_int] * 10 + [P]),
+        'ver_sca_backward': (c_int, [c_int, P, c_int, P, c_int, P, P, P, P, P, P, P] + [c_int] * 10 + [P]),
         'ver_feat_embed': (c_int, [c_int, P, P, P, P, c_int, c_int, c_int, c_int, P]),
         'ver_add_layernorm': (c_int, [c_int, P, P, P, P, P, c_int64, c_int, c_float, P]),
         'ver_focal_loss': (c_int, [P, P, c_int, P, P, P, P, c_int64, c_int, c_float, c_float, P]),

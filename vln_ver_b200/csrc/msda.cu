@@ -74,7 +74,7 @@ msda_bwd_staged(const T* __restrict__ value, const float* __restrict__ loc,
     BwdSmem<T, CPL> sm(smem_raw, S);
     const int bv = blockIdx.y, h = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bwd_prologue<T, CPL>(sm, value + ((size_t)bv * S * NH + h) * Dh, S, NH, lane, warp);
+    bwd_prologue<T, CPL>(sm, value + ((size_t)bv * S * NH + h) * Dh, S, (size_t)NH * Dh, lane, warp);
 
     const int corner = lane >> 3, g = lane & 7;
     for (int q = 0; q < Nq; ++q) {
@@ -94,7 +94,7 @@ msda_bwd_staged(const T* __restrict__ value, const float* __restrict__ loc,
             reinterpret_cast<float2*>(gloc)[qh * NP + g] = make_float2(gr.y, gr.z);
         }
     }
-    bwd_epilogue<T, CPL>(sm, gvalue + ((size_t)bv * S * NH + h) * Dh, S, NH, Sw, lane, warp);
+    bwd_epilogue<T, CPL>(sm, gvalue + ((size_t)bv * S * NH + h) * Dh, S, (size_t)NH * Dh, Sw, lane, warp);
 }
 
 struct LevelTable {

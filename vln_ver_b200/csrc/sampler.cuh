@@ -134,3 +134,31 @@ __device__ __forceinline__ void stage_tile_rows(T* tile, const T* gsrc, int S, i
         bulk_g2s(tile + (size_t)s * dst_row_elems, gsrc + (size_t)s * src_row_elems,
                  (uint32_t)(Dh * sizeof(T)), bar);
 }
+
+// where the [S][Dh] map of (view bv, head h) lives: base + bv*s_bv + h*s_h, rows s_row apart
+struct MapLayout {
+    size_t s_bv, s_h, s_row;
+};
+inline MapLayout make_layout(int layout, int S, int NH, int Dh) {
+    MapLayout L;
+    if (layout == VER_LAYOUT_HEAD_MAJOR) {       // [Bv][NH][S][Dh]
+        L.s_bv = (size_t)NH * S * Dh; L.s_h = (size_t)S * Dh; L.s_row = Dh;
+    } else {                                     // [Bv][S][NH][Dh]  (mmcv)
+        L.s_bv = (size_t)S * NH * Dh; L.s_h = Dh; L.s_row = (size_t)NH * Dh;
+    }
+    return L;
+}
+
+// one bulk copy when the map is contiguous in global memory, else one per pixel row
+template <typename T>
+__device__ __forceinline__ void stage_map(T* tile, const T* gsrc, int S, int Dh, size_t s_row,
+                                          uint64_t* bar, int lane) {
+    if (s_row == (size_t)Dh) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)(S * Dh * sizeof(T)));
+            bulk_g2s(tile, gsrc, (uint32_t)(S * Dh * sizeof(T)), bar);
+        }
+    } else {
+        stage_tile_rows(tile, gsrc, S, Dh, s_row, Dh, bar, lane);
+    }
+}

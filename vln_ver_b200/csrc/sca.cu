@@ -2,13 +2,15 @@
 // (M/spatial_cross_attention.py:138-173) with MSDeformableAttention3D's softmax and
 // location arithmetic (:340-374) folded in.
 //
-// Forward is voxel-tile centric: a CTA owns a compact TZ x TH x TW block of voxels
-// and one head.  It walks the cameras that see any voxel of the block in ascending
-// order (the reference's accumulation order), stages that camera's
-// [S][Dh] value map in shared memory with bulk async copies, lets its warps sample
-// the visible voxels, and keeps the per-voxel sums in shared memory; the
-// count-normalised slots are written exactly once.  No padded rebatch, no per-hit
-// intermediate, no atomics, no host sync.
+// Forward is voxel-tile centric: a CTA (16 warps) owns a compact 4 x 8 x 8 block of
+// voxels and one head.  It walks the cameras that see any voxel of the block in
+// ascending order (the reference's accumulation order), stages that
+// camera's [S][Dh] value map in shared memory with the bulk-copy (TMA) engine --
+// double buffered for fp16 maps, so the next camera streams in while the current
+// one is sampled -- lets its warps sample the visible voxels (compacted per camera),
+// and keeps the per-voxel sums in shared memory; the count-normalised slots are
+// written exactly once.  No padded rebatch, no per-hit intermediate, no atomics, no
+// host sync.
 //
 // Backward is camera centric (one CTA per (view, head), see sca_bwd.cuh) so that
 // grad_value never needs atomics; the per-voxel logit gradients (<= Ncam addends,
@@ -17,40 +19,47 @@
 
 namespace {
 
-constexpr int kFwdThreads = 256;
+constexpr int kFwdThreads = 512;
 constexpr int kFwdWarps = kFwdThreads / 32;
-constexpr int kTZ = 4, kTH = 4, kTW = 8;
-constexpr int kTV = kTZ * kTH * kTW;   // voxels per CTA
+constexpr int kTZ = 4, kTH = 8, kTW = 8;
+constexpr int kTV = kTZ * kTH * kTW;   // 256 voxels per CTA
+constexpr int kMaxCam = 32;
 
 template <typename T, int CPL>
 struct FwdSmem {
     static constexpr int Dh = CPL * 8;
+    static constexpr int NBUF = sizeof(T) == 2 ? 2 : 1;
     __host__ __device__ static size_t tile_bytes(int S) { return ((size_t)S * Dh * sizeof(T) + 127) / 128 * 128; }
     __host__ __device__ static size_t bytes(int S) {
-        return tile_bytes(S) + (size_t)kTV * Dh * sizeof(float)   // acc
-               + (size_t)kTV * 16 * sizeof(float)                 // offsets (8 x float2)
-               + (size_t)kTV * 8 * sizeof(float)                  // softmaxed weights
-               + (size_t)kTV * 2 * sizeof(int);                   // voxel id, visibility bits
+        return NBUF * tile_bytes(S) + (size_t)kTV * Dh * sizeof(float)   // acc
+               + (size_t)kTV * 16 * sizeof(float)                        // offsets (8 x float2)
+               + (size_t)kTV * 8 * sizeof(float)                         // softmaxed weights
+               + (size_t)kTV * 2 * sizeof(int)                           // voxel id, visibility bits
+               + (size_t)kMaxCam * kTV                                   // per-camera voxel lists (u8)
+               + (size_t)kMaxCam * sizeof(int);                          // per-camera counts
     }
 };
 
 template <typename T, int CPL>
-__global__ void __launch_bounds__(kFwdThreads)
-sca_fwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, int ld,
+__global__ void __launch_bounds__(kFwdThreads, 1)
+sca_fwd_kernel(const T* __restrict__ value, MapLayout L, const float* __restrict__ logits, int ld,
                const float* __restrict__ rpc, const uint32_t* __restrict__ vis_bits,
                T* __restrict__ slots, int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int NH,
                int NP) {
     constexpr int Dh = CPL * 8;
+    constexpr int NBUF = FwdSmem<T, CPL>::NBUF;
     const int S = Sh * Sw;
     const int Nq = Z * H * W;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* tile = reinterpret_cast<T*>(smem_raw);
-    float* s_acc = reinterpret_cast<float*>(smem_raw + FwdSmem<T, CPL>::tile_bytes(S));
+    const size_t tb = FwdSmem<T, CPL>::tile_bytes(S);
+    float* s_acc = reinterpret_cast<float*>(smem_raw + NBUF * tb);
     float* s_off = s_acc + kTV * Dh;
     float* s_aw = s_off + kTV * 16;
     int* s_n = reinterpret_cast<int*>(s_aw + kTV * 8);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_n + kTV);
-    __shared__ __align__(8) uint64_t bar;
+    uint8_t* s_list = reinterpret_cast<uint8_t*>(s_bits + kTV);
+    int* s_cnt = reinterpret_cast<int*>(s_list + kMaxCam * kTV);
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t s_union;
 
     const int b = blockIdx.z, h = blockIdx.y;
@@ -60,12 +69,14 @@ sca_fwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, in
               tz = blockIdx.x / (tiles_w * tiles_h);
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
         s_union = 0;
     }
+    if (threadIdx.x < kMaxCam) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    // ---- phase 0: voxel ids + visibility of the block
+    // ---- phase 0: voxel ids, visibility, per-camera voxel lists of the block
     if (threadIdx.x < kTV) {
         const int v = threadIdx.x;
         const int w = tw * kTW + (v % kTW), hh = th * kTH + (v / kTW) % kTH,
@@ -79,11 +90,20 @@ sca_fwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, in
         s_n[v] = n;
         s_bits[v] = bits;
         if (bits) atomicOr(&s_union, bits);
+        for (uint32_t r = bits; r; r &= r - 1) {
+            const int c = __ffs(r) - 1;
+            s_list[c * kTV + atomicAdd(&s_cnt[c], 1)] = (uint8_t)v;   // order inside a camera is free
+        }
     }
     for (int i = threadIdx.x; i < kTV * Dh / 4; i += kFwdThreads)
         reinterpret_cast<float4*>(s_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const uint32_t cams = s_union;
+    const T* vbase = value + (size_t)b * Ncam * L.s_bv + (size_t)h * L.s_h;
+    // first camera's map starts streaming in while the prologue computes the softmaxes
+    if (cams && warp == 0)
+        stage_map(reinterpret_cast<T*>(smem_raw), vbase + (size_t)(__ffs(cams) - 1) * L.s_bv, S, Dh,
+                  L.s_row, &bar[0], lane);
     // ---- phase 1: per-voxel offsets and softmax(attention logits) of this head
     {
         const int p = lane & 7;
@@ -113,20 +133,29 @@ sca_fwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, in
             s_aw[v * 8 + p] = e / s;
         }
     }
+    __syncthreads();
     // ---- phase 2: cameras in ascending order
     const int corner = lane >> 3, g = lane & 7;
-    uint32_t phase = 0;
-    for (uint32_t rest = cams; rest; rest &= rest - 1) {
+    int k = 0;
+    for (uint32_t rest = cams; rest; rest &= rest - 1, ++k) {
         const int c = __ffs(rest) - 1;
-        __syncthreads();                 // tile is free, phase-1 results visible
-        if (warp == 0)
-            stage_tile_rows(tile, value + (((size_t)(b * Ncam + c) * S) * NH + h) * Dh, S, Dh,
-                            (size_t)NH * Dh, Dh, &bar, lane);
-        mbar_wait(&bar, phase);
-        phase ^= 1;
+        const int buf = (NBUF == 2) ? (k & 1) : 0;
+        const T* tile = reinterpret_cast<const T*>(smem_raw + buf * tb);
+        if (NBUF == 2) {
+            const uint32_t nxt = rest & (rest - 1);
+            if (nxt && warp == 0)     // buffer (k+1)&1 was released by the barrier ending iteration k-1
+                stage_map(reinterpret_cast<T*>(smem_raw + ((k + 1) & 1) * tb),
+                          vbase + (size_t)(__ffs(nxt) - 1) * L.s_bv, S, Dh, L.s_row, &bar[(k + 1) & 1], lane);
+            mbar_wait(&bar[buf], (k >> 1) & 1);
+        } else {
+            if (k > 0 && warp == 0)
+                stage_map(reinterpret_cast<T*>(smem_raw), vbase + (size_t)c * L.s_bv, S, Dh, L.s_row, &bar[0], lane);
+            mbar_wait(&bar[0], k & 1);
+        }
         const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)c * B + b) * Nq;
-        for (int v = warp; v < kTV; v += kFwdWarps) {
-            if (!((s_bits[v] >> c) & 1u)) continue;
+        const int cnt = s_cnt[c];
+        for (int j = warp; j < cnt; j += kFwdWarps) {
+            const int v = s_list[c * kTV + j];
             const float2 ref = rp[s_n[v]];
             const float lx = ref.x + s_off[v * 16 + 2 * g];
             const float ly = ref.y + s_off[v * 16 + 2 * g + 1];
@@ -134,24 +163,24 @@ sca_fwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, in
             const Tap tap = make_tap(lx, ly, aw, corner, Sh, Sw, Dh);
             float acc[CPL];
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) acc[k] = 0.f;
+            for (int q = 0; q < CPL; ++q) acc[q] = 0.f;
             gather8<CPL>(tile, tap, lane, NP, acc);
             reduce_corners<CPL>(acc);
             if (lane < 8) {
                 float4* dst = reinterpret_cast<float4*>(s_acc + v * Dh + g * CPL);
 #pragma unroll
-                for (int k = 0; k < CPL / 4; ++k) {
-                    float4 o = dst[k];
-                    o.x += acc[4 * k];
-                    o.y += acc[4 * k + 1];
-                    o.z += acc[4 * k + 2];
-                    o.w += acc[4 * k + 3];
-                    dst[k] = o;
+                for (int q = 0; q < CPL / 4; ++q) {
+                    float4 o = dst[q];
+                    o.x += acc[4 * q];
+                    o.y += acc[4 * q + 1];
+                    o.z += acc[4 * q + 2];
+                    o.w += acc[4 * q + 3];
+                    dst[q] = o;
                 }
             }
         }
+        __syncthreads();                 // this camera's map and accumulator updates are retired
     }
-    __syncthreads();
     // ---- phase 3: slots = sum / max(count, 1)   (spatial_cross_attention.py:170-173)
     for (int i = threadIdx.x; i < kTV * (Dh / 4); i += kFwdThreads) {
         const int v = i / (Dh / 4), c4 = (i % (Dh / 4)) * 4;
@@ -167,7 +196,7 @@ sca_fwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, in
 // ------------------------------------------------------------------ backward
 template <typename T, int CPL>
 __global__ void __launch_bounds__(kBwdThreads, 2)
-sca_bwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, int ld,
+sca_bwd_kernel(const T* __restrict__ value, MapLayout L, const float* __restrict__ logits, int ld,
                const float* __restrict__ rpc, const uint32_t* __restrict__ vis_bits,
                const int32_t* __restrict__ counts, const int32_t* __restrict__ index,
                const T* __restrict__ gslots, float* __restrict__ gvalue,
@@ -179,7 +208,7 @@ sca_bwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, in
     const int bv = blockIdx.y, h = blockIdx.x;
     const int b = bv / Ncam, cam = bv % Ncam;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bwd_prologue<T, CPL>(sm, value + ((size_t)bv * S * NH + h) * Dh, S, NH, lane, warp);
+    bwd_prologue<T, CPL>(sm, value + (size_t)bv * L.s_bv + (size_t)h * L.s_h, S, L.s_row, lane, warp);
 
     const int corner = lane >> 3, g = lane & 7;
     const int nitems = counts[bv];
@@ -225,11 +254,11 @@ sca_bwd_kernel(const T* __restrict__ value, const float* __restrict__ logits, in
             }
         }
     }
-    bwd_epilogue<T, CPL>(sm, gvalue + ((size_t)bv * S * NH + h) * Dh, S, NH, Sw, lane, warp);
+    bwd_epilogue<T, CPL>(sm, gvalue + (size_t)bv * L.s_bv + (size_t)h * L.s_h, S, L.s_row, Sw, lane, warp);
 }
 
 template <typename T, int CPL>
-int launch_sca_fwd(const T* value, const float* logits, int ld, const float* rpc,
+int launch_sca_fwd(const T* value, int layout, const float* logits, int ld, const float* rpc,
                    const uint32_t* vis_bits, T* slots, int B, int Ncam, int Z, int H, int W, int Sh,
                    int Sw, int NH, int NP, cudaStream_t st) {
     const size_t smem = FwdSmem<T, CPL>::bytes(Sh * Sw);
@@ -239,15 +268,15 @@ int launch_sca_fwd(const T* value, const float* logits, int ld, const float* rpc
     VER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = ((W + kTW - 1) / kTW) * ((H + kTH - 1) / kTH) * ((Z + kTZ - 1) / kTZ);
     dim3 grid(tiles, NH, B);
-    kern<<<grid, kFwdThreads, smem, st>>>(value, logits, ld, rpc, vis_bits, slots, B, Ncam, Z, H, W, Sh,
-                                          Sw, NH, NP);
+    kern<<<grid, kFwdThreads, smem, st>>>(value, make_layout(layout, Sh * Sw, NH, CPL * 8), logits, ld,
+                                          rpc, vis_bits, slots, B, Ncam, Z, H, W, Sh, Sw, NH, NP);
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;
 }
 
 template <typename T, int CPL>
-int launch_sca_bwd(const T* value, const float* logits, int ld, const float* rpc,
+int launch_sca_bwd(const T* value, int layout, const float* logits, int ld, const float* rpc,
                    const uint32_t* vis_bits, const int32_t* counts, const int32_t* index,
                    const T* gslots, float* gvalue, float* glogits, int B, int Ncam, int Nq, int Sh,
                    int Sw, int NH, int NP, cudaStream_t st) {
@@ -259,20 +288,23 @@ int launch_sca_bwd(const T* value, const float* logits, int ld, const float* rpc
     VER_CHECK_CUDA(cudaMemset2DAsync(glogits, (size_t)ld * sizeof(float), 0,
                                      (size_t)NH * NP * 3 * sizeof(float), (size_t)B * Nq, st));
     dim3 grid(NH, B * Ncam);
-    kern<<<grid, kBwdThreads, smem, st>>>(value, logits, ld, rpc, vis_bits, counts, index, gslots,
-                                          gvalue, glogits, B, Ncam, Nq, Sh, Sw, NH, NP);
+    kern<<<grid, kBwdThreads, smem, st>>>(value, make_layout(layout, Sh * Sw, NH, CPL * 8), logits, ld, rpc,
+                                          vis_bits, counts, index, gslots, gvalue, glogits, B, Ncam, Nq,
+                                          Sh, Sw, NH, NP);
     VER_CHECK_LAUNCH();
     g_ver_launches += 2;
     return VER_OK;
 }
 
-int check_sca(int dtype, int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int NH, int Dh, int NP,
-              int ld) {
+int check_sca(int dtype, int layout, const void* value, int B, int Ncam, int Z, int H, int W, int Sh,
+              int Sw, int NH, int Dh, int NP, int ld) {
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
+    VER_CHECK_ARG(layout == VER_LAYOUT_MMCV || layout == VER_LAYOUT_HEAD_MAJOR, "bad value layout %d", layout);
     VER_CHECK_ARG(B > 0 && Ncam > 0 && Z > 0 && H > 0 && W > 0 && Sh > 0 && Sw > 0 && NH > 0,
                   "non-positive dimension");
     VER_CHECK_ARG(ld >= NH * NP * 3, "ld_logits %d < NH*NP*3 = %d", ld, NH * NP * 3);
-    if (Ncam > 32 || NP < 1 || NP > 8 || !(Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128) ||
+    VER_CHECK_ARG(((uintptr_t)value & 15) == 0, "value must be 16-byte aligned");
+    if (Ncam > kMaxCam || NP < 1 || NP > 8 || !(Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128) ||
         Sh * Sw > 65535) {
         ver_set_error("fused SCA supports Ncam<=32, NP<=8, Dh in {32,64,96,128}; got Ncam=%d NP=%d Dh=%d",
                       Ncam, NP, Dh);
@@ -291,39 +323,39 @@ int check_sca(int dtype, int B, int Ncam, int Z, int H, int W, int Sh, int Sw, i
         default: { constexpr int CPL = 16; return CALL; } \
     }
 
-extern "C" int ver_sca_forward(int dtype, const void* value, const float* logits, int ld_logits,
-                               const float* rpc, const uint32_t* vis_bits, void* slots, int B,
-                               int Ncam, int Z, int H, int W, int Sh, int Sw, int NH, int Dh, int NP,
-                               ver_stream_t stream) {
+extern "C" int ver_sca_forward(int dtype, const void* value, int value_layout, const float* logits,
+                               int ld_logits, const float* rpc, const uint32_t* vis_bits, void* slots,
+                               int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int NH, int Dh,
+                               int NP, ver_stream_t stream) {
     VER_CHECK_ARG(value && logits && rpc && vis_bits && slots, "null pointer");
-    int rc = check_sca(dtype, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
+    int rc = check_sca(dtype, value_layout, value, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == VER_F32) {
-        DISPATCH_CPL(Dh, (launch_sca_fwd<float, CPL>((const float*)value, logits, ld_logits, rpc, vis_bits,
-                                                     (float*)slots, B, Ncam, Z, H, W, Sh, Sw, NH, NP, st)));
+        DISPATCH_CPL(Dh, (launch_sca_fwd<float, CPL>((const float*)value, value_layout, logits, ld_logits, rpc,
+                                                     vis_bits, (float*)slots, B, Ncam, Z, H, W, Sh, Sw, NH, NP, st)));
     }
-    DISPATCH_CPL(Dh, (launch_sca_fwd<__half, CPL>((const __half*)value, logits, ld_logits, rpc, vis_bits,
-                                                  (__half*)slots, B, Ncam, Z, H, W, Sh, Sw, NH, NP, st)));
+    DISPATCH_CPL(Dh, (launch_sca_fwd<__half, CPL>((const __half*)value, value_layout, logits, ld_logits, rpc,
+                                                  vis_bits, (__half*)slots, B, Ncam, Z, H, W, Sh, Sw, NH, NP, st)));
 }
 
-extern "C" int ver_sca_backward(int dtype, const void* value, const float* logits, int ld_logits,
-                                const float* rpc, const uint32_t* vis_bits, const int32_t* counts,
-                                const int32_t* index, const void* grad_slots, float* grad_value,
-                                float* grad_logits, int B, int Ncam, int Z, int H, int W, int Sh,
-                                int Sw, int NH, int Dh, int NP, ver_stream_t stream) {
+extern "C" int ver_sca_backward(int dtype, const void* value, int value_layout, const float* logits,
+                                int ld_logits, const float* rpc, const uint32_t* vis_bits,
+                                const int32_t* counts, const int32_t* index, const void* grad_slots,
+                                float* grad_value, float* grad_logits, int B, int Ncam, int Z, int H,
+                                int W, int Sh, int Sw, int NH, int Dh, int NP, ver_stream_t stream) {
     VER_CHECK_ARG(value && logits && rpc && vis_bits && counts && index && grad_slots && grad_value &&
                       grad_logits, "null pointer");
-    int rc = check_sca(dtype, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
+    int rc = check_sca(dtype, value_layout, value, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int Nq = Z * H * W;
     if (dtype == VER_F32) {
-        DISPATCH_CPL(Dh, (launch_sca_bwd<float, CPL>((const float*)value, logits, ld_logits, rpc, vis_bits,
-                                                     counts, index, (const float*)grad_slots, grad_value,
-                                                     grad_logits, B, Ncam, Nq, Sh, Sw, NH, NP, st)));
+        DISPATCH_CPL(Dh, (launch_sca_bwd<float, CPL>((const float*)value, value_layout, logits, ld_logits, rpc,
+                                                     vis_bits, counts, index, (const float*)grad_slots,
+                                                     grad_value, grad_logits, B, Ncam, Nq, Sh, Sw, NH, NP, st)));
     }
-    DISPATCH_CPL(Dh, (launch_sca_bwd<__half, CPL>((const __half*)value, logits, ld_logits, rpc, vis_bits,
-                                                  counts, index, (const __half*)grad_slots, grad_value,
-                                                  grad_logits, B, Ncam, Nq, Sh, Sw, NH, NP, st)));
+    DISPATCH_CPL(Dh, (launch_sca_bwd<__half, CPL>((const __half*)value, value_layout, logits, ld_logits, rpc,
+                                                  vis_bits, counts, index, (const __half*)grad_slots,
+                                                  grad_value, grad_logits, B, Ncam, Nq, Sh, Sw, NH, NP, st)));
 }

@@ -73,7 +73,7 @@ __device__ __forceinline__ int swz_word(int pix, int sw, int c, int Dh) {
 }
 
 template <typename T, int CPL>
-__device__ __forceinline__ void bwd_prologue(BwdSmem<T, CPL>& sm, const T* gsrc, int S, int NH,
+__device__ __forceinline__ void bwd_prologue(BwdSmem<T, CPL>& sm, const T* gsrc, int S, size_t s_row,
                                              int lane, int warp) {
     constexpr int Dh = CPL * 8;
     if (threadIdx.x == 0) {
@@ -83,7 +83,7 @@ __device__ __forceinline__ void bwd_prologue(BwdSmem<T, CPL>& sm, const T* gsrc,
     for (int i = threadIdx.x; i < S * Dh / 4; i += kBwdThreads)
         reinterpret_cast<float4*>(sm.grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    if (warp == 0) stage_tile_rows(sm.val, gsrc, S, Dh, (size_t)NH * Dh, Dh, sm.bar, lane);
+    if (warp == 0) stage_map(sm.val, gsrc, S, Dh, s_row, sm.bar, lane);
     mbar_wait(sm.bar, 0);
 }
 
@@ -147,9 +147,9 @@ __device__ __forceinline__ float3 bwd_process_item(BwdSmem<T, CPL>& sm, const Ta
     return r;
 }
 
-// un-swizzle and write the finished grad_value map: gdst[(pix*NH)*Dh + c]
+// un-swizzle and write the finished grad_value map: gdst[pix*s_row + c]
 template <typename T, int CPL>
-__device__ __forceinline__ void bwd_epilogue(BwdSmem<T, CPL>& sm, float* gdst, int S, int NH,
+__device__ __forceinline__ void bwd_epilogue(BwdSmem<T, CPL>& sm, float* gdst, int S, size_t s_row,
                                              int Sw, int lane, int warp) {
     constexpr int Dh = CPL * 8;
     __syncthreads();
@@ -158,6 +158,6 @@ __device__ __forceinline__ void bwd_epilogue(BwdSmem<T, CPL>& sm, float* gdst, i
         const int pix = i / vec_per_row, c = (i % vec_per_row) * 4;
         const int sw = ((pix % Sw) & 1) | (((pix / Sw) & 1) << 1);
         const float4 v = *reinterpret_cast<const float4*>(sm.grad + swz_word(pix, sw, c, Dh));
-        *reinterpret_cast<float4*>(gdst + (size_t)pix * NH * Dh + c) = v;
+        *reinterpret_cast<float4*>(gdst + (size_t)pix * s_row + c) = v;
     }
 }

@@ -102,12 +102,11 @@ class SpatialCrossAttention(PrecisionMixin, BaseModule):
 
         cd = self.compute_dtype or query.dtype
         # value_proj on (bs*Ncam, S, C): view b*Ncam + cam (:158-161, :336)
-        projected = kwargs.get('value_is_projected_for')
-        if projected is not None and projected is self:
-            v = value
-        else:
-            v = value.permute(2, 0, 1, 3).reshape(bs * num_cams, l, embed_dims)
-            v = self._linear(v, da.value_proj, cd)
+        v = value.permute(2, 0, 1, 3).reshape(bs * num_cams, l, embed_dims)
+        v = self._linear(v, da.value_proj, cd)
+        # head-major maps [Bv][NH][S][Dh]: each (view, head) map is one contiguous 37.6 KB block,
+        # i.e. a single bulk (TMA) copy into shared memory instead of 196 row copies
+        v = v.view(bs * num_cams, l, da.num_heads, -1).permute(0, 2, 1, 3).contiguous()
         # one GEMM for sampling_offsets (+) attention_weights, once per VOXEL (:340-343)
         w_cat = torch.cat([da.sampling_offsets.weight, da.attention_weights.weight], 0)
         b_cat = torch.cat([da.sampling_offsets.bias, da.attention_weights.bias], 0)
@@ -117,7 +116,7 @@ class SpatialCrossAttention(PrecisionMixin, BaseModule):
         else:
             # low-precision product only for the data-dependent part; bias joins in fp32
             logits = F.linear(q2.to(cd), w_cat.to(cd)).float() + b_cat
-        slots = ops.sca_sample(v, logits, vis, Sh, Sw, da.num_heads, da.num_points)
+        slots = ops.sca_sample(v, logits, vis, Sh, Sw, da.num_heads, da.num_points, head_major=True)
         slots = self._linear(slots, self.output_proj, cd)
         return self.dropout(slots) + inp_residual.to(slots.dtype)
 

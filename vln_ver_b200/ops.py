@@ -191,15 +191,19 @@ class SCASampleFunction(Function):
     """slots = fused sampler(value, logits) -- see ver_sca_forward in include/ver_b200.h."""
 
     @staticmethod
-    def forward(ctx, value, logits, vis, Sh, Sw, NH, NP):
+    def forward(ctx, value, logits, vis, Sh, Sw, NH, NP, head_major=False):
+        """value: (Bv, S, NH, Dh) / (Bv, S, C) [mmcv layout] or (Bv, NH, S, Dh) if head_major."""
         _need_cuda(value, logits)
         value = _c(value)
         logits = _c(logits, torch.float32)
-        Bv, S, C = value.shape[0], value.shape[1], value.shape[2:].numel()
+        Bv = value.shape[0]
+        S = value.shape[2] if head_major else value.shape[1]
+        C = value[0].numel() // S
         Z, H, W = vis.grid
         Ncam, B = vis.rpc.shape[:2]
         assert Bv == B * Ncam and S == Sh * Sw
         Dh = C // NH
+        layout = 1 if head_major else 0
         Nq = Z * H * W
         assert logits.shape[0] == B * Nq
         if vis.bits is None:
@@ -209,14 +213,14 @@ class SCASampleFunction(Function):
         if prof is not None:          # bench.py: CUDA events on the launching stream around the kernel
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.ver_sca_forward(_code(value.dtype), _ptr(value), _ptr(logits), logits.shape[1],
+        check(lib.ver_sca_forward(_code(value.dtype), _ptr(value), layout, _ptr(logits), logits.shape[1],
                                   _ptr(vis.rpc), _ptr(vis.bits), _ptr(slots), B, Ncam, Z, H, W, Sh, Sw,
                                   NH, Dh, NP, _stream()))
         if prof is not None:
             e1.record()
             prof.append((e0, e1))
         ctx.save_for_backward(value, logits)
-        ctx.vis, ctx.dims = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP)
+        ctx.vis, ctx.dims = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, layout)
         return slots
 
     @staticmethod
@@ -224,22 +228,22 @@ class SCASampleFunction(Function):
     def backward(ctx, grad_slots):
         value, logits = ctx.saved_tensors
         vis = ctx.vis
-        B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP = ctx.dims
+        B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, layout = ctx.dims
         counts, index = vis.index
         gs = _c(grad_slots, value.dtype)
         gvalue = torch.empty(value.shape, dtype=torch.float32, device=value.device)
         glogits = torch.empty(logits.shape, dtype=torch.float32, device=value.device)
         if logits.shape[1] > NH * NP * 3:
             glogits[:, NH * NP * 3:].zero_()
-        check(lib.ver_sca_backward(_code(value.dtype), _ptr(value), _ptr(logits), logits.shape[1],
+        check(lib.ver_sca_backward(_code(value.dtype), _ptr(value), layout, _ptr(logits), logits.shape[1],
                                    _ptr(vis.rpc), _ptr(vis.bits), _ptr(counts), _ptr(index), _ptr(gs),
                                    _ptr(gvalue), _ptr(glogits), B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP,
                                    _stream()))
-        return gvalue.to(value.dtype), glogits, None, None, None, None, None
+        return gvalue.to(value.dtype), glogits, None, None, None, None, None, None
 
 
-def sca_sample(value, logits, vis, Sh, Sw, NH, NP):
-    return SCASampleFunction.apply(value, logits, vis, Sh, Sw, NH, NP)
+def sca_sample(value, logits, vis, Sh, Sw, NH, NP, head_major=False):
+    return SCASampleFunction.apply(value, logits, vis, Sh, Sw, NH, NP, head_major)
 
 
 # ------------------------------------------------------------------ A8 prologue, A6 epilogue
