@@ -40,6 +40,9 @@ extern "C" {
 /* layout of per-view feature maps handed to the fused SCA entry points */
 #define VER_LAYOUT_MMCV 0       /* [Bv][S][NH][Dh]  (what mmcv's op takes) */
 #define VER_LAYOUT_HEAD_MAJOR 1 /* [Bv][NH][S][Dh]  (one contiguous map per (view, head): single bulk copy) */
+#define VER_LAYOUT_TC_IMAGE 2   /* output of ver_value_image_f16: tensor-core operand image, selects the
+                                   tcgen05 sampler (fp16 only); with this layout ver_sca_backward writes
+                                   grad_value in VER_LAYOUT_MMCV order */
 
 typedef void* ver_stream_t; /* cudaStream_t */
 
@@ -117,6 +120,11 @@ int ver_msda_backward(int dtype, const void* value, const int32_t* shapes_hw, in
 int ver_sca_forward(int dtype, const void* value, int value_layout, const float* logits, int ld_logits,
                     const float* rpc, const uint32_t* vis_bits, void* slots, int B, int Ncam, int Z,
                     int H, int W, int Sh, int Sw, int NH, int Dh, int NP, ver_stream_t stream);
+
+/* Re-lays fp16 value maps out as tcgen05 operand images (one per (view, head)):
+ *   value [Bv, S, NH, Dh] fp16 (VER_LAYOUT_MMCV)  ->  vimg [Bv, NH, Dh/8, SP/8, 8, 8] fp16,
+ *   SP = S rounded up to 16, padded pixels zero.  Dh % 8 == 0. */
+int ver_value_image_f16(const void* value, void* vimg, int Bv, int S, int NH, int Dh, ver_stream_t stream);
 
 /* Backward of ver_sca_forward.
  *   grad_slots  [B, Nq, NH*Dh] dtype

@@ -281,6 +281,56 @@ def test_focal_loss_vs_oracle():
     assert rel_err(xc.grad, xr.grad) < 1e-5
 
 
+# ------------------------------------------------------------------ tcgen05 sampler vs oracle
+def _oracle_sample(value, logits, rpc, mask, count, B, Ncam, Nq, NH, Dh, NP=8, S=14):
+    """per-(b, cam) hits through the restated 2-D sampler, scatter-mean over cameras (fp64)."""
+    v = value.double().view(B, Ncam, S * S, NH, Dh)
+    lg = logits.double().view(B, Nq, -1)
+    off = lg[..., :NH * NP * 2].view(B, Nq, NH, 1, NP, 2) / S
+    aw = lg[..., NH * NP * 2:NH * NP * 3].view(B, Nq, NH, NP).softmax(-1).view(B, Nq, NH, 1, NP)
+    out = torch.zeros(B, Nq, NH * Dh, dtype=torch.float64)
+    for b in range(B):
+        for c in range(Ncam):
+            idx = mask[c, b, :, 0].nonzero().squeeze(-1)
+            if len(idx) == 0:
+                continue
+            loc = rpc[c, b, idx].double().view(1, -1, 1, 1, 1, 2) + off[b, idx][None]
+            o = ver_ref.multi_scale_deformable_attn_pytorch(v[b, c][None], torch.tensor([[S, S]]), loc,
+                                                            aw[b, idx][None])
+            out[b, idx] += o[0]
+    return out / count.double().clamp(min=1)[..., None]
+
+
+@pytest.mark.parametrize('Dh,grid,B', [(96, (8, 20, 20), 2), (32, (3, 5, 7), 1), (128, (4, 8, 8), 1)])
+def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B):
+    ncam, NH = 18, 8
+    Nq = grid[0] * grid[1] * grid[2]
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=11)
+    rpc, mask, bits, count = ops.point_sampling(cuda(torch.from_numpy(l2i)), cuda(torch.from_numpy(sh)), PC, *grid)
+    vis = ops.Visibility(rpc, mask, bits, count, grid)
+    g = torch.Generator().manual_seed(5)
+    value = (torch.randn(B * ncam, 196, NH * Dh, generator=g) * 0.5).half()
+    logits = torch.randn(B * Nq, 192, generator=g)
+    logits[:, :128] *= 2.0
+    gout = torch.randn(B, Nq, NH * Dh, generator=g).half()
+    # oracle (fp64 on the fp16-rounded inputs) with autograd
+    v64 = value.double().requires_grad_(True)
+    l64 = logits.double().requires_grad_(True)
+    ref = _oracle_sample(v64, l64, rpc.cpu(), mask.cpu(), count.cpu(), B, ncam, Nq, NH, Dh)
+    gv_r, gl_r = torch.autograd.grad(ref, (v64, l64), gout.double())
+    # tensor-core path
+    vc = cuda(value).requires_grad_(True)
+    lc = cuda(logits).requires_grad_(True)
+    out = ops.sca_sample_tc(vc, lc, vis, 14, 14, NH, 8)
+    assert rel_err(out, ref) < 1e-3
+    out.backward(cuda(gout))
+    assert rel_err(vc.grad, gv_r) < 2e-3
+    assert rel_err(lc.grad, gl_r) < 2e-3
+    # and the gather kernels agree with it
+    out_g = ops.sca_sample(cuda(value).view(B * ncam, 196, NH, Dh), cuda(logits), vis, 14, 14, NH, 8)
+    assert rel_err(out, out_g) < 1e-3
+
+
 # ------------------------------------------------------------------ size-independent properties
 def test_full_size_properties():
     """BASELINE config-2/3 shape (18 views, 16x40x40): linearity of the sampler in `value`,

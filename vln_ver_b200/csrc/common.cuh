@@ -33,6 +33,15 @@ void ver_set_error(const char* fmt, ...);
 #define VER_CHECK_LAUNCH() VER_CHECK_CUDA(cudaGetLastError())
 
 extern std::atomic<int64_t> g_ver_launches;
+// tensor-core (tcgen05) sampler, sca_tc.cu
+int ver_tc_supported(int Ncam, int S, int Dh, int NP);
+int ver_sca_forward_tc(const void* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
+                       void* slots, int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int NH, int Dh, int NP,
+                       cudaStream_t st);
+int ver_sca_backward_tc(const void* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
+                        const int32_t* counts, const int32_t* index, const void* gslots, float* gvalue,
+                        float* glogits, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
+                        cudaStream_t st);
 int ver_device_sm_count();
 int ver_device_max_smem_optin();
 

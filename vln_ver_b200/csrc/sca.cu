@@ -328,9 +328,19 @@ extern "C" int ver_sca_forward(int dtype, const void* value, int value_layout, c
                                int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int NH, int Dh,
                                int NP, ver_stream_t stream) {
     VER_CHECK_ARG(value && logits && rpc && vis_bits && slots, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (value_layout == VER_LAYOUT_TC_IMAGE) {
+        int rc = check_sca(dtype, VER_LAYOUT_MMCV, value, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
+        if (rc) return rc;
+        if (dtype != VER_F16 || !ver_tc_supported(Ncam, Sh * Sw, Dh, NP)) {
+            ver_set_error("tensor-core sampler needs fp16 maps, S <= 256, Dh in {32,64,96,128}");
+            return VER_ERR_UNSUPPORTED;
+        }
+        return ver_sca_forward_tc(value, logits, ld_logits, rpc, vis_bits, slots, B, Ncam, Z, H, W, Sh, Sw, NH, Dh,
+                                  NP, st);
+    }
     int rc = check_sca(dtype, value_layout, value, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
     if (dtype == VER_F32) {
         DISPATCH_CPL(Dh, (launch_sca_fwd<float, CPL>((const float*)value, value_layout, logits, ld_logits, rpc,
                                                      vis_bits, (float*)slots, B, Ncam, Z, H, W, Sh, Sw, NH, NP, st)));
@@ -346,10 +356,20 @@ extern "C" int ver_sca_backward(int dtype, const void* value, int value_layout, 
                                 int W, int Sh, int Sw, int NH, int Dh, int NP, ver_stream_t stream) {
     VER_CHECK_ARG(value && logits && rpc && vis_bits && counts && index && grad_slots && grad_value &&
                       grad_logits, "null pointer");
-    int rc = check_sca(dtype, value_layout, value, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int Nq = Z * H * W;
+    if (value_layout == VER_LAYOUT_TC_IMAGE) {
+        int rc = check_sca(dtype, VER_LAYOUT_MMCV, value, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
+        if (rc) return rc;
+        if (dtype != VER_F16 || !ver_tc_supported(Ncam, Sh * Sw, Dh, NP)) {
+            ver_set_error("tensor-core sampler needs fp16 maps, S <= 256, Dh in {32,64,96,128}");
+            return VER_ERR_UNSUPPORTED;
+        }
+        return ver_sca_backward_tc(value, logits, ld_logits, rpc, vis_bits, counts, index, grad_slots, grad_value,
+                                   grad_logits, B, Ncam, Nq, Sh, Sw, NH, Dh, NP, st);
+    }
+    int rc = check_sca(dtype, value_layout, value, B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, ld_logits);
+    if (rc) return rc;
     if (dtype == VER_F32) {
         DISPATCH_CPL(Dh, (launch_sca_bwd<float, CPL>((const float*)value, value_layout, logits, ld_logits, rpc,
                                                      vis_bits, counts, index, (const float*)grad_slots,

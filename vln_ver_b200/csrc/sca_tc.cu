@@ -1,0 +1,664 @@
+// Tensor-core (tcgen05 / TMEM) formulation of the fused SCA sampler, fp16 storage.
+//
+// Deformable sampling over ONE 14x14 map is a contraction with a sparse interpolation matrix:
+//     out[row, ch] = sum_pix A[row, pix] * V[pix, ch],     A[row, pix] = sum_taps aw * bilinear
+// with 32 taps (8 points x 4 corners) per (voxel|hit, head) row and only S = 196 "keys".
+// Gathering the taps from shared memory costs ~300 issue slots per row (measured: the gather
+// kernels are issue/LSU bound at <5% of the HBM roofline); building the row of A (32 scalar
+// read-modify-writes) and letting the 5th-gen tensor cores do the dense K = 208 contraction
+// costs ~15.  Forward:  O = A V  accumulated over cameras in TMEM (ascending camera order, fp32).
+// Backward (per view, head, chunks of 128 hits):  dV^T = G^T A'   and   Dots = G V^T,
+// from which d/d(attention logits) and d/d(offsets) are read back at the 32 taps of each row.
+//
+// Shared-memory operand images use the canonical no-swizzle core-matrix layout (8 rows x 16 B
+// contiguous); one image serves as K-major or MN-major operand depending on which index is
+// called "K" (validated on hardware with tools/tc_probe.cu):
+//     V image  [ch/8][pix/8][ch%8][pix%8]   (built once per layer by value_image_kernel)
+//     A image  [row/8][pix/8][row%8][pix%8]
+//     G image  [hit/8][ch/8][hit%8][ch%8]
+// Descriptor convention: LBO = byte stride between core matrices along K, SBO = along M/N.
+#include "sca_bwd.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- tcgen05 / TMEM primitives
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t k_stride_bytes, uint32_t mn_stride_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((k_stride_bytes >> 4) & 0x3FFF) << 16;     // leading-dimension byte offset
+    d |= (uint64_t)((mn_stride_bytes >> 4) & 0x3FFF) << 32;    // stride-dimension byte offset
+    d |= (uint64_t)1 << 46;                                    // sm_100 descriptor version
+    return d;                                                  // swizzle: none
+}
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4)                              // D format fp32
+           | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+           | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // A/B format fp16 (0)
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db),
+        "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 32 lanes x 16 consecutive fp32 columns; the warp must own TMEM lane quarter (warp_id % 4)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// element offset (halves) in a core-matrix image whose "row" index has `groups_k` 8-wide groups
+// along the contiguous index:   [row/8][k/8][row%8][k%8]
+__device__ __forceinline__ int img_off(int row, int k, int groups_k) {
+    return ((row >> 3) * groups_k + (k >> 3)) * 64 + (row & 7) * 8 + (k & 7);
+}
+
+// ---------------------------------------------------------------- value image
+// value [Bv][S][NH][Dh] fp16  ->  vimg [Bv][NH][Dh/8][SP/8][8][8] fp16, pixels >= S zero
+__global__ void value_image_kernel(const __half* __restrict__ value, __half* __restrict__ vimg, int Bv,
+                                   int S, int NH, int Dh, int SP) {
+    // one thread per 16-byte output chunk = (bv, h, ch/8, pix/8, ch%8): 8 pixels of one channel
+    const size_t chunks = (size_t)Bv * NH * (Dh / 8) * (SP / 8) * 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < chunks;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int c8 = i & 7;
+        size_t r = i >> 3;
+        const int pg = r % (SP / 8);
+        r /= (SP / 8);
+        const int cg = r % (Dh / 8);
+        r /= (Dh / 8);
+        const int h = r % NH;
+        const int bv = r / NH;
+        const int ch = cg * 8 + c8;
+        __half out[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int pix = pg * 8 + p;
+            out[p] = pix < S ? value[(((size_t)bv * S + pix) * NH + h) * Dh + ch] : __float2half(0.f);
+        }
+        *reinterpret_cast<uint4*>(vimg + i * 8) = *reinterpret_cast<const uint4*>(out);
+    }
+}
+
+// ---------------------------------------------------------------- forward
+constexpr int kTcThreads = 512;
+constexpr int kTcWarps = kTcThreads / 32;
+constexpr int kTZ = 4, kTH = 8, kTW = 8;
+constexpr int kTV = kTZ * kTH * kTW;        // 256 voxel rows = two M=128 halves
+constexpr int kMaxCam = 32;
+
+struct TcFwdSmem {
+    // byte offsets inside dynamic shared memory
+    int v_bytes, a_half_bytes;
+    int off_v0, off_v1, off_a0, off_a1, off_soff, off_saw, off_n, off_bits, off_list, off_cnt, total;
+    __host__ __device__ TcFwdSmem(int Dh, int SP) {
+        v_bytes = Dh * SP * 2;
+        a_half_bytes = 128 * SP * 2;
+        off_v0 = 0;
+        off_v1 = off_v0 + v_bytes;
+        off_a0 = off_v1 + v_bytes;
+        off_a1 = off_a0 + a_half_bytes;
+        off_soff = off_a1 + a_half_bytes;
+        off_saw = off_soff + kTV * 16 * 4;
+        off_n = off_saw + kTV * 8 * 4;
+        off_bits = off_n + kTV * 4;
+        off_list = off_bits + kTV * 4;
+        off_cnt = off_list + kMaxCam * kTV;
+        total = off_cnt + kMaxCam * 4;
+    }
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ logits, int ld,
+                  const float* __restrict__ rpc, const uint32_t* __restrict__ vis_bits,
+                  __half* __restrict__ slots, int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int SP,
+                  int NH, int NP) {
+    const int Nq = Z * H * W;
+    const int G = SP >> 3;                       // 8-pixel groups per row
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcFwdSmem L(DH, SP);
+    float* s_off = reinterpret_cast<float*>(smem + L.off_soff);
+    float* s_aw = reinterpret_cast<float*>(smem + L.off_saw);
+    int* s_n = reinterpret_cast<int*>(smem + L.off_n);
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.off_bits);
+    uint8_t* s_list = smem + L.off_list;
+    int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
+    __shared__ __align__(8) uint64_t bar_v[2], bar_mma[2];
+    __shared__ uint32_t s_union, s_tmem;
+
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_w = (W + kTW - 1) / kTW, tiles_h = (H + kTH - 1) / kTH;
+    const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h,
+              tz = blockIdx.x / (tiles_w * tiles_h);
+
+    if (tid == 0) {
+        mbar_init(&bar_v[0], 1);
+        mbar_init(&bar_v[1], 1);
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        mbar_fence_init();
+        s_union = 0;
+    }
+    if (tid < kMaxCam) s_cnt[tid] = 0;
+    if (warp == 1) tmem_alloc(&s_tmem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    // ---- voxel ids, visibility, per-camera voxel lists
+    if (tid < kTV) {
+        const int v = tid;
+        const int w = tw * kTW + (v % kTW), hh = th * kTH + (v / kTW) % kTH, z = tz * kTZ + v / (kTW * kTH);
+        int n = -1;
+        uint32_t bits = 0;
+        if (w < W && hh < H && z < Z) {
+            n = (z * H + hh) * W + w;
+            bits = vis_bits[(size_t)b * Nq + n];
+        }
+        s_n[v] = n;
+        s_bits[v] = bits;
+        if (bits) atomicOr(&s_union, bits);
+        for (uint32_t r = bits; r; r &= r - 1) {
+            const int c = __ffs(r) - 1;
+            s_list[c * kTV + atomicAdd(&s_cnt[c], 1)] = (uint8_t)v;
+        }
+    }
+    __syncthreads();
+    const uint32_t cams = s_union;
+    const size_t v_stride_bv = (size_t)NH * DH * SP;         // halves per view
+    const __half* vbase = vimg + (size_t)b * Ncam * v_stride_bv + (size_t)h * DH * SP;
+    if (tid == 0 && cams) {                                  // first two camera maps start streaming in
+        const int c0 = __ffs(cams) - 1;
+        mbar_expect_tx(&bar_v[0], L.v_bytes);
+        bulk_g2s(smem + L.off_v0, vbase + (size_t)c0 * v_stride_bv, L.v_bytes, &bar_v[0]);
+        const uint32_t r1 = cams & (cams - 1);
+        if (r1) {
+            const int c1 = __ffs(r1) - 1;
+            mbar_expect_tx(&bar_v[1], L.v_bytes);
+            bulk_g2s(smem + L.off_v1, vbase + (size_t)c1 * v_stride_bv, L.v_bytes, &bar_v[1]);
+        }
+    }
+    // ---- per-voxel offsets / softmax of this head (as in the gather kernel)
+    {
+        const int p = lane & 7;
+        for (int v = tid >> 3; v < kTV; v += kTcThreads / 8) {
+            const int n = s_n[v];
+            if (n < 0 || s_bits[v] == 0) continue;
+            const float* row = logits + ((size_t)b * Nq + n) * ld;
+            float2 off = make_float2(0.f, 0.f);
+            float lg = -INFINITY;
+            if (p < NP) {
+                off = reinterpret_cast<const float2*>(row + h * NP * 2)[p];
+                lg = row[NH * NP * 2 + h * NP + p];
+            }
+            const unsigned gm = 0xffu << (lane & 24);
+            float m = lg;
+            m = fmaxf(m, __shfl_xor_sync(gm, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(gm, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(gm, m, 4));
+            const float e = (p < NP) ? expf(lg - m) : 0.f;
+            float s = e;
+            s += __shfl_xor_sync(gm, s, 1);
+            s += __shfl_xor_sync(gm, s, 2);
+            s += __shfl_xor_sync(gm, s, 4);
+            s_off[v * 16 + 2 * p] = off.x / (float)Sw;
+            s_off[v * 16 + 2 * p + 1] = off.y / (float)Sh;
+            s_aw[v * 8 + p] = e / s;
+        }
+    }
+    __syncthreads();
+
+    constexpr uint32_t idesc = umma_idesc(128, DH, 0, 0);
+    // ---- cameras in ascending order; two 128-row halves pipeline build (threads) against MMA (async)
+    int k = 0;
+    for (uint32_t rest = cams; rest; rest &= rest - 1, ++k) {
+        const int c = __ffs(rest) - 1;
+        const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)c * B + b) * Nq;
+        const int cnt = s_cnt[c];
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+            __half* A = reinterpret_cast<__half*>(smem + (hf ? L.off_a1 : L.off_a0));
+            if (k > 0) mbar_wait(&bar_mma[hf], (k - 1) & 1);      // previous camera's MMAs on this half retired
+            if (hf == 1 && k > 0 && tid == 0) {
+                // both halves of camera k-1 retired -> its V buffer ((k+1)&1) is free: prefetch camera k+1
+                const uint32_t nxt = rest & (rest - 1);
+                if (nxt) {
+                    const int cn = __ffs(nxt) - 1;
+                    mbar_expect_tx(&bar_v[(k + 1) & 1], L.v_bytes);
+                    bulk_g2s(smem + (((k + 1) & 1) ? L.off_v1 : L.off_v0), vbase + (size_t)cn * v_stride_bv,
+                             L.v_bytes, &bar_v[(k + 1) & 1]);
+                }
+            }
+            tc_fence_after();
+            for (int i = tid; i < L.a_half_bytes / 16; i += kTcThreads)
+                reinterpret_cast<uint4*>(A)[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            // one thread per visible voxel of this half; entries are dealt round-robin to the warps
+            const int j = (tid & 31) * kTcWarps + (tid >> 5);
+            if (j < cnt) {
+                const int v = s_list[c * kTV + j];
+                if ((v >> 7) == hf) {
+                    const int r = v & 127;
+                    const float2 ref = rp[s_n[v]];
+                    for (int p = 0; p < NP; ++p) {
+                        const float aw = s_aw[v * 8 + p];
+                        const float x = (ref.x + s_off[v * 16 + 2 * p]) * (float)Sw - 0.5f;
+                        const float y = (ref.y + s_off[v * 16 + 2 * p + 1]) * (float)Sh - 0.5f;
+                        if (!(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
+                        const float xf = floorf(x), yf = floorf(y);
+                        const float fx = x - xf, fy = y - yf;
+                        const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+                        for (int cn = 0; cn < 4; ++cn) {
+                            const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                            if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                            const float wgt = aw * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
+                            __half* a = A + img_off(r, yi * Sw + xi, G);
+                            *a = __float2half_rn(__half2float(*a) + wgt);
+                        }
+                    }
+                }
+            }
+            proxy_fence();                       // generic-proxy writes of A -> async proxy (tensor core)
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                if (hf == 0) mbar_wait(&bar_v[k & 1], (k >> 1) & 1);          // this camera's V image landed
+                const uint32_t a_addr = smem_u32(A);
+                const uint32_t v_addr = smem_u32(smem + ((k & 1) ? L.off_v1 : L.off_v0));
+                for (int ks = 0; ks < SP / 16; ++ks)
+                    umma_f16(tmem + hf * DH, umma_desc(a_addr + ks * 256, 128, G * 128),
+                             umma_desc(v_addr + ks * 256, 128, G * 128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
+                umma_commit(&bar_mma[hf]);
+            }
+        }
+    }
+    // ---- epilogue: slots = sum / max(count, 1)
+    if (cams) {
+        mbar_wait(&bar_mma[0], (k - 1) & 1);
+        mbar_wait(&bar_mma[1], (k - 1) & 1);
+    }
+    tc_fence_after();
+    {
+        const int q = warp & 3, grp = warp >> 2;          // TMEM lane quarter, column group
+        const int hf = grp >> 1, cpart = grp & 1;         // 4 groups = 2 halves x 2 channel halves
+        const int v = hf * 128 + q * 32 + lane;
+        const int n = s_n[v];
+        const float inv_is_div = (float)max(__popc(s_bits[v]), 1);
+        constexpr int CH = DH / 2;                        // channels per thread
+        __half* dst = (n >= 0) ? slots + ((size_t)b * Nq + n) * NH * DH + h * DH + cpart * CH : nullptr;
+#pragma unroll
+        for (int c0 = 0; c0 < CH; c0 += 16) {
+            float vv[16];
+            if (cams) {
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + hf * DH + cpart * CH + c0, vv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vv[i] = 0.f;
+            }
+            if (dst) {
+                float o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = vv[i] / inv_is_div;
+                store_channels<16>(dst + c0, o);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------- backward
+constexpr int kBtThreads = 256;
+constexpr int kHitsPerChunk = 128;
+
+struct TcBwdSmem {
+    int v_bytes, a_bytes, g_bytes;
+    int off_v, off_a, off_g, off_n, total;
+    __host__ __device__ TcBwdSmem(int Dh, int SP) {
+        v_bytes = Dh * SP * 2;
+        a_bytes = kHitsPerChunk * SP * 2;               // also reused as the fp32 Dots staging buffer
+        g_bytes = kHitsPerChunk * Dh * 2 + 1024;        // + slack: M=128 over-reads past ch < Dh
+        off_v = 0;
+        off_a = off_v + v_bytes;
+        off_g = off_a + a_bytes;
+        off_n = off_g + g_bytes;
+        total = off_n + kHitsPerChunk * 4;
+    }
+};
+
+struct HitTaps {          // per-point quantities a thread recomputes for "its" hit
+    float aw, x, y;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(kBtThreads, 1)
+sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ logits, int ld,
+                  const float* __restrict__ rpc, const uint32_t* __restrict__ vis_bits,
+                  const int32_t* __restrict__ counts, const int32_t* __restrict__ index,
+                  const __half* __restrict__ gslots, float* __restrict__ gvalue,
+                  float* __restrict__ glogits, int B, int Ncam, int Nq, int Sh, int Sw, int SP, int NH,
+                  int NP) {
+    const int S = Sh * Sw;
+    const int G = SP >> 3;
+    constexpr int CG = DH / 8;                           // channel groups
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcBwdSmem L(DH, SP);
+    __half* Aimg = reinterpret_cast<__half*>(smem + L.off_a);
+    float* dots = reinterpret_cast<float*>(smem + L.off_a);      // reused after the MMAs retire
+    __half* Gimg = reinterpret_cast<__half*>(smem + L.off_g);
+    int* s_n = reinterpret_cast<int*>(smem + L.off_n);
+    __shared__ __align__(8) uint64_t bar_v, bar_mma;
+    __shared__ uint32_t s_tmem;
+
+    const int bv = blockIdx.y, h = blockIdx.x;
+    const int b = bv / Ncam, cam = bv % Ncam;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(&bar_v, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(&s_tmem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t tm_dv = tmem;                  // dV^T : lanes = channel, columns [0, SP) = pixel
+    const uint32_t tm_dots = tmem + 256;          // Dots : lanes = hit,     columns [0, SP) = pixel
+    if (tid == 0) {
+        mbar_expect_tx(&bar_v, L.v_bytes);
+        bulk_g2s(smem + L.off_v, vimg + ((size_t)bv * NH + h) * DH * SP, L.v_bytes, &bar_v);
+    }
+    const int nitems = counts[bv];
+    const int32_t* idx = index + (size_t)bv * Nq;
+    const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)cam * B + b) * Nq;
+    constexpr uint32_t idesc_dv = umma_idesc(128, 0, 1, 1);       // N patched in at run time (SP)
+    constexpr uint32_t idesc_dots = umma_idesc(128, 0, 0, 1);
+    const uint32_t n_bits = (uint32_t)(SP >> 3) << 17;
+
+    uint32_t phase = 0;
+    const int nchunks = (nitems + kHitsPerChunk - 1) / kHitsPerChunk;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int base = chunk * kHitsPerChunk;
+        const int rows = min(kHitsPerChunk, nitems - base);
+        // ---- zero A', publish the chunk's voxel ids
+        for (int i = tid; i < L.a_bytes / 16; i += kBtThreads)
+            reinterpret_cast<uint4*>(Aimg)[i] = make_uint4(0, 0, 0, 0);
+        if (tid < kHitsPerChunk) s_n[tid] = tid < rows ? idx[base + tid] : -1;
+        __syncthreads();
+        // ---- G image: gather grad_slots rows (16-byte chunks = 8 channels of one hit)
+        for (int i = tid; i < kHitsPerChunk * CG; i += kBtThreads) {
+            const int r = i / CG, cg = i % CG;
+            const int n = s_n[r];
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (n >= 0)
+                val = *reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH + cg * 8);
+            *reinterpret_cast<uint4*>(Gimg + ((r >> 3) * CG + cg) * 64 + (r & 7) * 8) = val;
+        }
+        // ---- A' rows: thread per hit (threads 0..127)
+        float p_aw[8], p_x[8], p_y[8];
+        float inv_cnt = 0.f;
+        int my_n = -1;
+        if (tid < kHitsPerChunk) {
+            my_n = s_n[tid];
+            if (my_n >= 0) {
+                const int r = tid;
+                const float* row = logits + ((size_t)b * Nq + my_n) * ld;
+                float lg[8], mx = -INFINITY;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    lg[p] = p < NP ? row[NH * NP * 2 + h * NP + p] : -INFINITY;
+                    mx = fmaxf(mx, lg[p]);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    lg[p] = p < NP ? expf(lg[p] - mx) : 0.f;
+                    sum += lg[p];
+                }
+                const float2 ref = rp[my_n];
+                inv_cnt = 1.f / (float)max(__popc(vis_bits[(size_t)b * Nq + my_n]), 1);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    float2 off = make_float2(0.f, 0.f);
+                    if (p < NP) off = reinterpret_cast<const float2*>(row + h * NP * 2)[p];
+                    p_aw[p] = lg[p] / sum;
+                    p_x[p] = (ref.x + off.x / (float)Sw) * (float)Sw - 0.5f;
+                    p_y[p] = (ref.y + off.y / (float)Sh) * (float)Sh - 0.5f;
+                    const float x = p_x[p], y = p_y[p];
+                    if (p >= NP || !(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
+                    const float xf = floorf(x), yf = floorf(y);
+                    const float fx = x - xf, fy = y - yf;
+                    const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                        if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                        const float wgt = inv_cnt * p_aw[p] * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
+                        __half* a = Aimg + img_off(r, yi * Sw + xi, G);
+                        *a = __float2half_rn(__half2float(*a) + wgt);
+                    }
+                }
+            }
+        }
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            if (chunk == 0) mbar_wait(&bar_v, 0);
+            const uint32_t a_addr = smem_u32(Aimg), g_addr = smem_u32(Gimg), v_addr = smem_u32(smem + L.off_v);
+            // dV^T[ch, pix] += G^T[ch, hit] A'[hit, pix]   (A: G image MN-major; B: A' image MN-major)
+            for (int ks = 0; ks < kHitsPerChunk / 16; ++ks)
+                umma_f16(tm_dv, umma_desc(g_addr + ks * 2 * CG * 128, CG * 128, 128),
+                         umma_desc(a_addr + ks * 2 * G * 128, G * 128, 128), idesc_dv | n_bits,
+                         (chunk > 0 || ks > 0) ? 1u : 0u);
+            // Dots[hit, pix] = G[hit, ch] V[pix, ch]^T     (A: G image K-major; B: V image MN-major)
+            for (int ks = 0; ks < DH / 16; ++ks)
+                umma_f16(tm_dots, umma_desc(g_addr + ks * 256, 128, CG * 128),
+                         umma_desc(v_addr + ks * 2 * G * 128, G * 128, 128), idesc_dots | n_bits, ks > 0 ? 1u : 0u);
+            umma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- Dots: TMEM -> shared (fp32, two column halves through the retired A' buffer), then
+        //      every hit thread picks its 32 taps
+        float ga[8], gx[8], gy[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) ga[p] = gx[p] = gy[p] = 0.f;
+        const int half_cols = ((SP / 2 + 15) / 16) * 16;         // 112 for SP = 208
+        for (int part = 0; part < 2; ++part) {
+            const int col0 = part * half_cols;
+            const int ncols = min(half_cols, SP - col0);
+            if (warp < 4) {
+                for (int c0 = 0; c0 < ncols; c0 += 16) {
+                    float vv[16];
+                    tmem_ld16(tm_dots + ((uint32_t)(warp * 32) << 16) + col0 + c0, vv);
+                    float4* d = reinterpret_cast<float4*>(dots + tid * half_cols + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+                }
+            }
+            __syncthreads();
+            if (tid < kHitsPerChunk && my_n >= 0) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const float x = p_x[p], y = p_y[p];
+                    if (p >= NP || !(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
+                    const float xf = floorf(x), yf = floorf(y);
+                    const float fx = x - xf, fy = y - yf;
+                    const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                        if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                        const int pix = yi * Sw + xi;
+                        if (pix < col0 || pix >= col0 + ncols) continue;
+                        const float d = dots[tid * half_cols + pix - col0];
+                        const float wx = (cn & 1) ? fx : 1.f - fx, wy = (cn >> 1) ? fy : 1.f - fy;
+                        ga[p] += wy * wx * d;
+                        gx[p] += ((cn & 1) ? wy : -wy) * d;
+                        gy[p] += ((cn >> 1) ? wx : -wx) * d;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- softmax backward + accumulate into the per-voxel logit gradients
+        if (tid < kHitsPerChunk && my_n >= 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                ga[p] *= inv_cnt;
+                t += p_aw[p] * ga[p];
+            }
+            float* grow = glogits + ((size_t)b * Nq + my_n) * ld;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                if (p >= NP) break;
+                atomicAdd(grow + NH * NP * 2 + h * NP + p, p_aw[p] * (ga[p] - t));
+                // d loc = aw * size * sum(...), d offset = d loc / size
+                atomicAdd(grow + h * NP * 2 + 2 * p, inv_cnt * p_aw[p] * (float)Sw * gx[p] / (float)Sw);
+                atomicAdd(grow + h * NP * 2 + 2 * p + 1, inv_cnt * p_aw[p] * (float)Sh * gy[p] / (float)Sh);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();           // A'/dots and G buffers are free for the next chunk
+        tc_fence_after();
+    }
+    // ---- grad_value: dV^T (TMEM lanes = channel) -> [bv][pix][h][ch] fp32
+    if (nchunks == 0 && tid == 0) mbar_wait(&bar_v, 0);       // never leave a bulk copy in flight
+    if (warp < 4) {
+        const int ch = warp * 32 + lane;
+        float* gdst = gvalue + ((size_t)bv * S * NH + h) * DH + ch;
+        for (int c0 = 0; c0 < SP; c0 += 16) {
+            float vv[16];
+            if (nchunks > 0) {
+                tmem_ld16(tm_dv + ((uint32_t)(warp * 32) << 16) + c0, vv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vv[i] = 0.f;
+            }
+            if (ch < DH) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < S) gdst[(size_t)(c0 + i) * NH * DH] = vv[i];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int DH>
+int launch_fwd_tc(const __half* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
+                  __half* slots, int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int SP, int NH, int NP,
+                  cudaStream_t st) {
+    const TcFwdSmem L(DH, SP);
+    VER_CHECK_ARG(L.total + 2048 <= ver_device_max_smem_optin(), "TC forward needs %d B of shared memory", L.total);
+    auto kern = sca_fwd_tc_kernel<DH>;
+    VER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    const int tiles = ((W + kTW - 1) / kTW) * ((H + kTH - 1) / kTH) * ((Z + kTZ - 1) / kTZ);
+    kern<<<dim3(tiles, NH, B), kTcThreads, L.total, st>>>(vimg, logits, ld, rpc, vis_bits, slots, B, Ncam, Z, H, W,
+                                                         Sh, Sw, SP, NH, NP);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+template <int DH>
+int launch_bwd_tc(const __half* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
+                  const int32_t* counts, const int32_t* index, const __half* gslots, float* gvalue,
+                  float* glogits, int B, int Ncam, int Nq, int Sh, int Sw, int SP, int NH, int NP,
+                  cudaStream_t st) {
+    const TcBwdSmem L(DH, SP);
+    VER_CHECK_ARG(L.total + 2048 <= ver_device_max_smem_optin(), "TC backward needs %d B of shared memory", L.total);
+    auto kern = sca_bwd_tc_kernel<DH>;
+    VER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    VER_CHECK_CUDA(cudaMemset2DAsync(glogits, (size_t)ld * sizeof(float), 0, (size_t)NH * NP * 3 * sizeof(float),
+                                     (size_t)B * Nq, st));
+    kern<<<dim3(NH, B * Ncam), kBtThreads, L.total, st>>>(vimg, logits, ld, rpc, vis_bits, counts, index, gslots,
+                                                         gvalue, glogits, B, Ncam, Nq, Sh, Sw, SP, NH, NP);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 2;
+    return VER_OK;
+}
+
+}  // namespace
+
+// ---- entry points used by sca.cu's dispatch (value_layout == VER_LAYOUT_TC_IMAGE) and the C ABI
+int ver_tc_supported(int Ncam, int S, int Dh, int NP) {
+    return Ncam <= kMaxCam && NP >= 1 && NP <= 8 && S <= 256 && (Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128);
+}
+
+extern "C" int ver_value_image_f16(const void* value, void* vimg, int Bv, int S, int NH, int Dh,
+                                   ver_stream_t stream) {
+    VER_CHECK_ARG(value && vimg, "null pointer");
+    VER_CHECK_ARG(Bv > 0 && S > 0 && NH > 0 && Dh > 0 && Dh % 8 == 0, "bad dims");
+    const int SP = (S + 15) / 16 * 16;
+    const size_t chunks = (size_t)Bv * NH * (Dh / 8) * (SP / 8) * 8;
+    const int blocks = (int)((chunks + 255) / 256 > 148 * 32 ? 148 * 32 : (chunks + 255) / 256);
+    value_image_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)value, (__half*)vimg, Bv, S, NH, Dh, SP);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+int ver_sca_forward_tc(const void* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
+                       void* slots, int B, int Ncam, int Z, int H, int W, int Sh, int Sw, int NH, int Dh, int NP,
+                       cudaStream_t st) {
+    const int SP = (Sh * Sw + 15) / 16 * 16;
+#define FWD(D) launch_fwd_tc<D>((const __half*)vimg, logits, ld, rpc, vis_bits, (__half*)slots, B, Ncam, Z, H, W, Sh, Sw, SP, NH, NP, st)
+    switch (Dh) {
+        case 32: return FWD(32);
+        case 64: return FWD(64);
+        case 96: return FWD(96);
+        default: return FWD(128);
+    }
+#undef FWD
+}
+
+int ver_sca_backward_tc(const void* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
+                        const int32_t* counts, const int32_t* index, const void* gslots, float* gvalue,
+                        float* glogits, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
+                        cudaStream_t st) {
+    const int SP = (Sh * Sw + 15) / 16 * 16;
+#define BWD(D) launch_bwd_tc<D>((const __half*)vimg, logits, ld, rpc, vis_bits, counts, index, (const __half*)gslots, gvalue, glogits, B, Ncam, Nq, Sh, Sw, SP, NH, NP, st)
+    switch (Dh) {
+        case 32: return BWD(32);
+        case 64: return BWD(64);
+        case 96: return BWD(96);
+        default: return BWD(128);
+    }
+#undef BWD
+}

@@ -41,6 +41,7 @@ class SpatialCrossAttention(PrecisionMixin, BaseModule):
         self.num_cams = num_cams
         self.output_proj = nn.Linear(embed_dims, embed_dims)
         self.batch_first = batch_first
+        self.sampler = 'auto'          # 'auto': tcgen05 sampler for fp16 maps, gather otherwise; 'gather'
         self.init_weight()
 
     def init_weight(self):
@@ -104,9 +105,12 @@ class SpatialCrossAttention(PrecisionMixin, BaseModule):
         # value_proj on (bs*Ncam, S, C): view b*Ncam + cam (:158-161, :336)
         v = value.permute(2, 0, 1, 3).reshape(bs * num_cams, l, embed_dims)
         v = self._linear(v, da.value_proj, cd)
-        # head-major maps [Bv][NH][S][Dh]: each (view, head) map is one contiguous 37.6 KB block,
-        # i.e. a single bulk (TMA) copy into shared memory instead of 196 row copies
-        v = v.view(bs * num_cams, l, da.num_heads, -1).permute(0, 2, 1, 3).contiguous()
+        use_tc = self.sampler != 'gather' and ops.tc_supported(
+            v.dtype, num_cams, l, embed_dims // da.num_heads, da.num_points)
+        if not use_tc:
+            # head-major maps [Bv][NH][S][Dh]: each (view, head) map is one contiguous block, i.e. a
+            # single bulk (TMA) copy into shared memory instead of 196 row copies
+            v = v.view(bs * num_cams, l, da.num_heads, -1).permute(0, 2, 1, 3).contiguous()
         # one GEMM for sampling_offsets (+) attention_weights, once per VOXEL (:340-343)
         w_cat = torch.cat([da.sampling_offsets.weight, da.attention_weights.weight], 0)
         b_cat = torch.cat([da.sampling_offsets.bias, da.attention_weights.bias], 0)
@@ -116,7 +120,10 @@ class SpatialCrossAttention(PrecisionMixin, BaseModule):
         else:
             # low-precision product only for the data-dependent part; bias joins in fp32
             logits = F.linear(q2.to(cd), w_cat.to(cd)).float() + b_cat
-        slots = ops.sca_sample(v, logits, vis, Sh, Sw, da.num_heads, da.num_points, head_major=True)
+        if use_tc:      # fp16 maps: interpolation-matrix x value on the tcgen05 tensor cores
+            slots = ops.sca_sample_tc(v, logits, vis, Sh, Sw, da.num_heads, da.num_points)
+        else:           # fp32 (parity mode) / unsupported shapes: shared-memory gather kernels
+            slots = ops.sca_sample(v, logits, vis, Sh, Sw, da.num_heads, da.num_points, head_major=True)
         slots = self._linear(slots, self.output_proj, cd)
         return self.dropout(slots) + inp_residual.to(slots.dtype)
 

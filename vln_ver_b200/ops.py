@@ -246,6 +246,82 @@ def sca_sample(value, logits, vis, Sh, Sw, NH, NP, head_major=False):
     return SCASampleFunction.apply(value, logits, vis, Sh, Sw, NH, NP, head_major)
 
 
+def value_image(value, NH):
+    """fp16 value maps (Bv, S, C) -> tcgen05 operand images (Bv, NH, Dh/8, SP/8, 8, 8)."""
+    _need_cuda(value)
+    assert value.dtype == torch.float16
+    value = _c(value)
+    Bv, S = value.shape[:2]
+    Dh = value[0].numel() // S // NH
+    SP = (S + 15) // 16 * 16
+    vimg = torch.empty((Bv, NH, Dh // 8, SP // 8, 8, 8), dtype=torch.float16, device=value.device)
+    check(lib.ver_value_image_f16(_ptr(value), _ptr(vimg), Bv, S, NH, Dh, _stream()))
+    return vimg
+
+
+VER_LAYOUT_TC_IMAGE = 2
+
+
+class SCASampleTCFunction(Function):
+    """Tensor-core (tcgen05) fused sampler, fp16 maps.  `value` is (Bv, S, C) in the mmcv layout (what
+    value_proj produces); the operand image is built here and kept for backward."""
+
+    @staticmethod
+    def forward(ctx, value, logits, vis, Sh, Sw, NH, NP):
+        _need_cuda(value, logits)
+        logits = _c(logits, torch.float32)
+        Bv, S = value.shape[:2]
+        C = value[0].numel() // S
+        Z, H, W = vis.grid
+        Ncam, B = vis.rpc.shape[:2]
+        assert Bv == B * Ncam and S == Sh * Sw
+        Dh, Nq = C // NH, Z * H * W
+        assert logits.shape[0] == B * Nq
+        if vis.bits is None:
+            raise VerError('fused SCA needs Ncam <= 32')
+        vimg = value_image(value, NH)
+        slots = torch.empty((B, Nq, C), dtype=torch.float16, device=value.device)
+        prof = PROFILE_EVENTS
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(lib.ver_sca_forward(VER_F16, _ptr(vimg), VER_LAYOUT_TC_IMAGE, _ptr(logits), logits.shape[1],
+                                  _ptr(vis.rpc), _ptr(vis.bits), _ptr(slots), B, Ncam, Z, H, W, Sh, Sw,
+                                  NH, Dh, NP, _stream()))
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1))
+        ctx.save_for_backward(vimg, logits)
+        ctx.vis, ctx.dims, ctx.vshape = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP), value.shape
+        return slots
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_slots):
+        vimg, logits = ctx.saved_tensors
+        vis = ctx.vis
+        B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP = ctx.dims
+        counts, index = vis.index
+        gs = _c(grad_slots, torch.float16)
+        gvalue = torch.empty(ctx.vshape, dtype=torch.float32, device=vimg.device)    # mmcv layout
+        glogits = torch.empty(logits.shape, dtype=torch.float32, device=vimg.device)
+        if logits.shape[1] > NH * NP * 3:
+            glogits[:, NH * NP * 3:].zero_()
+        check(lib.ver_sca_backward(VER_F16, _ptr(vimg), VER_LAYOUT_TC_IMAGE, _ptr(logits), logits.shape[1],
+                                   _ptr(vis.rpc), _ptr(vis.bits), _ptr(counts), _ptr(index), _ptr(gs),
+                                   _ptr(gvalue), _ptr(glogits), B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP,
+                                   _stream()))
+        return gvalue.to(torch.float16), glogits, None, None, None, None, None
+
+
+def sca_sample_tc(value, logits, vis, Sh, Sw, NH, NP):
+    return SCASampleTCFunction.apply(value, logits, vis, Sh, Sw, NH, NP)
+
+
+def tc_supported(dtype, Ncam, S, Dh, NP):
+    return dtype == torch.float16 and Ncam <= 32 and 1 <= NP <= 8 and S <= 256 and Dh in (32, 64, 96, 128)
+
+
 # ------------------------------------------------------------------ A8 prologue, A6 epilogue
 def feat_embed(feats, cams_embeds, level_embed, dtype=torch.float32):
     """(Ncam, B, S, C) fp32 + cams_embeds[cam] + level_embeds[0] -> (B*Ncam, S, C) `dtype`
