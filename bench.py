@@ -250,7 +250,7 @@ def run_b200(args):
         P = float(np.mean(counts))                       # visible (b, cam, voxel) pairs per launch
         B = args.batch
         bv = 2
-        bytes_min = (B * NCAM * 196 * EMBED * bv        # value maps, each read once
+        bytes_min = (B * NCAM * 208 * EMBED * bv        # value operand images (196 px padded to 208), read once
                      + B * Nq * 192 * 4                 # offset/weight logits, once per VOXEL
                      + P * 8 + B * Nq * 4               # reference points per hit, visibility bits
                      + B * Nq * EMBED * bv)             # slots written once
@@ -259,7 +259,8 @@ def run_b200(args):
         roof = None
         if sampler_ms:
             ach = bytes_min / (sampler_ms * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': 'sca_fwd_kernel<__half,12>', 'achieved': round(ach, 1),
+            roof = {'bound': 'hbm', 'kernel': 'sca_fwd_tc_kernel<96> (tcgen05 fused SCA sampler, forward)',
+                    'achieved': round(ach, 1),
                     'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'traffic': None,
                     'peak_source': peak_src, 'launch_ms': round(sampler_ms, 4),
                     'algorithmic_bytes': int(bytes_min),

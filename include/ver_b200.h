@@ -155,6 +155,27 @@ int ver_add_layernorm(int dtype, const void* x, const void* residual, const floa
                       const float* beta, void* y, int64_t rows, int C, float eps,
                       ver_stream_t stream);
 
+/* Training forms of the same epilogue (dropout p = 0.1 in vocc.py:135 / spatial_cross_attention.py:62):
+ *   z = residual + dropout(x, p) ;  y = LayerNorm(z) * gamma + beta
+ * with a counter-based Philox dropout mask that backward regenerates from (seed, element index).
+ *   z_out (dtype) and stats (float2 mean, rstd per row) are saved for backward; both may be NULL.
+ * Backward: dx = dz * keep/(1-p), dresidual = dz (may be NULL), and per-block partial sums of
+ *   dgamma / dbeta: [ver_dropout_add_layernorm_bwd_blocks(rows), C] fp32 each (caller sums over dim 0). */
+int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const void* residual, const float* gamma,
+                                  const float* beta, void* y, void* z_out, float* stats, int64_t rows,
+                                  int C, float eps, float p_drop, uint64_t seed, ver_stream_t stream);
+int ver_dropout_add_layernorm_bwd_blocks(int64_t rows);
+int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const void* z, const float* stats,
+                                  const float* gamma, void* dx, void* dresidual, float* dgamma_part,
+                                  float* dbeta_part, int64_t rows, int C, float p_drop, uint64_t seed,
+                                  ver_stream_t stream);
+/* FFN inner activation (mmcv FFN: Linear -> ReLU -> Dropout): h = dropout(relu(a)), in place allowed;
+ * backward da = dh * [h > 0] / (1 - p).  n % 8 == 0. */
+int ver_relu_dropout_fwd(int dtype, const void* a, void* h, int64_t n, float p_drop, uint64_t seed,
+                         ver_stream_t stream);
+int ver_relu_dropout_bwd(int dtype, const void* dh, const void* h, void* da, int64_t n, float p_drop,
+                         ver_stream_t stream);
+
 /* ---------------------------------------------------------------- A11
  * Sigmoid focal loss of mmdet FocalLoss(use_sigmoid=True) (vocc.py:190-195; calls HEAD:981,
  * HEAD:1425) with the dense target built on the fly from the sparse GT

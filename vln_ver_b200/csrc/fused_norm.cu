@@ -1,0 +1,400 @@
+// Training-path epilogues of VoxelFormerLayer (A6): HBM-bound row kernels that replace chains of
+// separate dropout / add / cast / LayerNorm / ReLU passes (measured: 28 ms of a 139 ms step were
+// such passes).  One warp per row, 16-byte vector accesses, fp32 statistics, counter-based
+// (Philox4x32-10) dropout so the mask is regenerated in backward instead of stored.
+//
+//   z = residual + dropout(x) ; y = LayerNorm(z) * gamma + beta          (SCA / FFN -> 'norm')
+//   h = dropout(relu(a))                                                  (FFN inner activation)
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t seed) {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask for 8 consecutive elements starting at flat element index e0 (e0 % 8 == 0):
+// one Philox call yields 128 random bits = 8 x 16-bit uniforms
+__device__ __forceinline__ uint32_t keep8(uint64_t e0, uint64_t seed, uint32_t thr16) {
+    const uint4 r = philox4x32(e0 >> 3, seed);
+    uint32_t m = 0;
+    m |= ((r.x & 0xffff) >= thr16) << 0;
+    m |= ((r.x >> 16) >= thr16) << 1;
+    m |= ((r.y & 0xffff) >= thr16) << 2;
+    m |= ((r.y >> 16) >= thr16) << 3;
+    m |= ((r.z & 0xffff) >= thr16) << 4;
+    m |= ((r.z >> 16) >= thr16) << 5;
+    m |= ((r.w & 0xffff) >= thr16) << 6;
+    m |= ((r.w >> 16) >= thr16) << 7;
+    return m;
+}
+
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<__half> {
+    uint4 raw;
+    __device__ __forceinline__ void load(const __half* p) { raw = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+    __device__ __forceinline__ void get(float (&f)[8]) const {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __half22float2(h[i]);
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        }
+    }
+    __device__ __forceinline__ void set(const float (&f)[8]) {
+        __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    }
+};
+template <>
+struct Vec8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = reinterpret_cast<const float4*>(p)[0];
+        b = reinterpret_cast<const float4*>(p)[1];
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        reinterpret_cast<float4*>(p)[0] = a;
+        reinterpret_cast<float4*>(p)[1] = b;
+    }
+    __device__ __forceinline__ void get(float (&f)[8]) const {
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    __device__ __forceinline__ void set(const float (&f)[8]) {
+        a = make_float4(f[0], f[1], f[2], f[3]);
+        b = make_float4(f[4], f[5], f[6], f[7]);
+    }
+};
+
+constexpr int kRowsPerBlock = 8;       // 8 warps, one row each per iteration
+
+// ---------------------------------------------------------------- forward
+// NV = 8-element vectors per lane (C = 256 * NV ... handled as C <= 32*8*NV with bounds checks)
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+dropout_add_ln_fwd(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ z_out,
+                   float2* __restrict__ stats, int64_t rows, int C, float eps, float p, uint64_t seed) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t thr16 = (uint32_t)(p * 65536.f);
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + warp; row < rows;
+         row += (int64_t)gridDim.x * kRowsPerBlock) {
+        float v[NV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+                Vec8<T> vx;
+                vx.load(x + row * C + c);
+                vx.get(v[k]);
+                if (p > 0.f) {
+                    const uint32_t m = keep8((uint64_t)row * C + c, seed, thr16);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[k][e] = ((m >> e) & 1) ? v[k][e] * scale : 0.f;
+                }
+                if (res) {
+                    Vec8<T> vr;
+                    float r[8];
+                    vr.load(res + row * C + c);
+                    vr.get(r);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[k][e] += r[e];
+                }
+                if (z_out) {      // the LN input as stored (rounded to T): backward recomputes from it
+                    Vec8<T> vz;
+                    vz.set(v[k]);
+                    vz.store(z_out + row * C + c);
+                    vz.get(v[k]);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sum += v[k][e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(VER_FULL_MASK, sum, o);
+        const float mean = sum / (float)C;
+        float var = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float d = v[k][e] - mean;
+                    var += d * d;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(VER_FULL_MASK, var, o);
+        const float rstd = rsqrtf(var / (float)C + eps);
+        if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (v[k][e] - mean) * rstd * gamma[c + e] + beta[c + e];
+                Vec8<T> vy;
+                vy.set(o);
+                vy.store(y + row * C + c);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- backward
+// dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// d residual = dz ; dx = dz * keep / (1-p) ; partial dgamma/dbeta per block
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const float2* __restrict__ stats,
+                   const float* __restrict__ gamma, T* __restrict__ dx, T* __restrict__ dres,
+                   float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows, int C,
+                   float p, uint64_t seed) {
+    extern __shared__ float s_part[];       // [2][8 warps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t thr16 = (uint32_t)(p * 65536.f);
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    float dg[NV][8], db[NV][8];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = 0.f;
+
+    for (int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + warp; row < rows;
+         row += (int64_t)gridDim.x * kRowsPerBlock) {
+        const float2 st = stats[row];
+        float g[NV][8], xh[NV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+                Vec8<T> a, b;
+                float fy[8], fz[8];
+                a.load(dy + row * C + c);
+                a.get(fy);
+                b.load(z + row * C + c);
+                b.get(fz);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    xh[k][e] = (fz[e] - st.x) * st.y;
+                    g[k][e] = fy[e] * gamma[c + e];
+                    s1 += g[k][e];
+                    s2 += g[k][e] * xh[k][e];
+                    dg[k][e] += fy[e] * xh[k][e];
+                    db[k][e] += fy[e];
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            s1 += __shfl_xor_sync(VER_FULL_MASK, s1, o);
+            s2 += __shfl_xor_sync(VER_FULL_MASK, s2, o);
+        }
+        const float m1 = s1 / (float)C, m2 = s2 / (float)C;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+                float dz[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dz[e] = st.y * (g[k][e] - m1 - xh[k][e] * m2);
+                Vec8<T> o;
+                if (dres) {
+                    o.set(dz);
+                    o.store(dres + row * C + c);
+                }
+                if (p > 0.f) {
+                    const uint32_t m = keep8((uint64_t)row * C + c, seed, thr16);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dz[e] = ((m >> e) & 1) ? dz[e] * scale : 0.f;
+                }
+                o.set(dz);
+                o.store(dx + row * C + c);
+            }
+        }
+    }
+    // block-level reduction of the parameter-gradient partials
+    float* sg = s_part;
+    float* sb = s_part + 8 * C;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int c = (k * 32 + lane) * 8;
+        if (c < C) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                sg[warp * C + c + e] = dg[k][e];
+                sb[warp * C + c + e] = db[k][e];
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            a += sg[w * C + c];
+            b += sb[w * C + c];
+        }
+        dgamma_part[(size_t)blockIdx.x * C + c] = a;
+        dbeta_part[(size_t)blockIdx.x * C + c] = b;
+    }
+}
+
+// ---------------------------------------------------------------- h = dropout(relu(a)), in place capable
+template <typename T>
+__global__ void __launch_bounds__(256)
+relu_dropout_fwd(const T* __restrict__ a, T* __restrict__ h, int64_t n8, float p, uint64_t seed) {
+    const uint32_t thr16 = (uint32_t)(p * 65536.f);
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec8<T> v;
+        float f[8];
+        v.load(a + i * 8);
+        v.get(f);
+        const uint32_t m = p > 0.f ? keep8((uint64_t)i * 8, seed, thr16) : 0xffu;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = (((m >> e) & 1) && f[e] > 0.f) ? f[e] * scale : 0.f;
+        v.set(f);
+        v.store(h + i * 8);
+    }
+}
+// da = dh * [h > 0] / (1 - p)   (a kept element with relu(a) == 0 has zero gradient either way)
+template <typename T>
+__global__ void __launch_bounds__(256)
+relu_dropout_bwd(const T* __restrict__ dh, const T* __restrict__ h, T* __restrict__ da, int64_t n8, float p) {
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec8<T> vg, vh;
+        float g[8], f[8];
+        vg.load(dh + i * 8);
+        vg.get(g);
+        vh.load(h + i * 8);
+        vh.get(f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = f[e] > 0.f ? g[e] * scale : 0.f;
+        vg.set(g);
+        vg.store(da + i * 8);
+    }
+}
+
+int ln_grid(int64_t rows) {
+    const int64_t need = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
+    const int cap = 148 * 4;
+    return (int)(need < cap ? (need ? need : 1) : cap);
+}
+
+}  // namespace
+
+#define LN_DISPATCH(KERN, T, nv, ...)                                   \
+    do {                                                                \
+        if (nv <= 1) KERN<T, 1> __VA_ARGS__;                            \
+        else if (nv <= 2) KERN<T, 2> __VA_ARGS__;                       \
+        else if (nv <= 3) KERN<T, 3> __VA_ARGS__;                       \
+        else KERN<T, 4> __VA_ARGS__;                                    \
+    } while (0)
+
+extern "C" int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const void* residual,
+                                             const float* gamma, const float* beta, void* y, void* z_out,
+                                             float* stats, int64_t rows, int C, float eps, float p_drop,
+                                             uint64_t seed, ver_stream_t stream) {
+    VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
+    VER_CHECK_ARG(x && gamma && beta && y, "null pointer");
+    VER_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 1024, "C must be a multiple of 8, <= 1024 (got %d)", C);
+    VER_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bad dropout probability");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nv = (C + 255) / 256;
+    const int grid = ln_grid(rows);
+    if (dtype == VER_F16)
+        LN_DISPATCH(dropout_add_ln_fwd, __half, nv, <<<grid, 256, 0, st>>>((const __half*)x, (const __half*)residual, gamma, beta, (__half*)y, (__half*)z_out, (float2*)stats, rows, C, eps, p_drop, seed));
+    else
+        LN_DISPATCH(dropout_add_ln_fwd, float, nv, <<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y, (float*)z_out, (float2*)stats, rows, C, eps, p_drop, seed));
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+extern "C" int ver_dropout_add_layernorm_bwd_blocks(int64_t rows) { return ln_grid(rows); }
+
+extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const void* z, const float* stats,
+                                             const float* gamma, void* dx, void* dresidual,
+                                             float* dgamma_part, float* dbeta_part, int64_t rows, int C,
+                                             float p_drop, uint64_t seed, ver_stream_t stream) {
+    VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
+    VER_CHECK_ARG(dy && z && stats && gamma && dx && dgamma_part && dbeta_part, "null pointer");
+    VER_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 1024, "C must be a multiple of 8, <= 1024 (got %d)", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nv = (C + 255) / 256;
+    const int grid = ln_grid(rows);
+    const size_t smem = (size_t)2 * 8 * C * sizeof(float);
+    if (dtype == VER_F16) {
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        LN_DISPATCH(dropout_add_ln_bwd, __half, nv, <<<grid, 256, smem, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, rows, C, p_drop, seed));
+    } else {
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(dropout_add_ln_bwd<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(dropout_add_ln_bwd<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        LN_DISPATCH(dropout_add_ln_bwd, float, nv, <<<grid, 256, smem, st>>>((const float*)dy, (const float*)z, (const float2*)stats, gamma, (float*)dx, (float*)dresidual, dgamma_part, dbeta_part, rows, C, p_drop, seed));
+    }
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+extern "C" int ver_relu_dropout_fwd(int dtype, const void* a, void* h, int64_t n, float p_drop, uint64_t seed,
+                                    ver_stream_t stream) {
+    VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
+    VER_CHECK_ARG(a && h && n > 0 && n % 8 == 0, "bad arguments (n %% 8 != 0?)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n8 = n / 8;
+    const int grid = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+    if (dtype == VER_F16) relu_dropout_fwd<__half><<<grid, 256, 0, st>>>((const __half*)a, (__half*)h, n8, p_drop, seed);
+    else relu_dropout_fwd<float><<<grid, 256, 0, st>>>((const float*)a, (float*)h, n8, p_drop, seed);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+extern "C" int ver_relu_dropout_bwd(int dtype, const void* dh, const void* h, void* da, int64_t n, float p_drop,
+                                    ver_stream_t stream) {
+    VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
+    VER_CHECK_ARG(dh && h && da && n > 0 && n % 8 == 0, "bad arguments (n %% 8 != 0?)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n8 = n / 8;
+    const int grid = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+    if (dtype == VER_F16) relu_dropout_bwd<__half><<<grid, 256, 0, st>>>((const __half*)dh, (const __half*)h, (__half*)da, n8, p_drop);
+    else relu_dropout_bwd<float><<<grid, 256, 0, st>>>((const float*)dh, (const float*)h, (float*)da, n8, p_drop);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}

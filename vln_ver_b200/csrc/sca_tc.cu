@@ -126,7 +126,7 @@ struct TcFwdSmem {
         off_bits = off_n + kTV * 4;
         off_list = off_bits + kTV * 4;
         off_cnt = off_list + kMaxCam * kTV;
-        total = off_cnt + kMaxCam * 4;
+        total = off_cnt + 2 * kMaxCam * 4;
     }
 };
 
@@ -163,7 +163,7 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
         mbar_fence_init();
         s_union = 0;
     }
-    if (tid < kMaxCam) s_cnt[tid] = 0;
+    if (tid < 2 * kMaxCam) s_cnt[tid] = 0;
     if (warp == 1) tmem_alloc(&s_tmem, 256);
     tc_fence_before();
     __syncthreads();
@@ -182,9 +182,9 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
         s_n[v] = n;
         s_bits[v] = bits;
         if (bits) atomicOr(&s_union, bits);
-        for (uint32_t r = bits; r; r &= r - 1) {
-            const int c = __ffs(r) - 1;
-            s_list[c * kTV + atomicAdd(&s_cnt[c], 1)] = (uint8_t)v;
+        for (uint32_t r = bits; r; r &= r - 1) {      // per (camera, 128-row half) lists of visible rows
+            const int c = __ffs(r) - 1, hf = v >> 7;
+            s_list[(c * 2 + hf) * 128 + atomicAdd(&s_cnt[c * 2 + hf], 1)] = (uint8_t)(v & 127);
         }
     }
     __syncthreads();
@@ -205,29 +205,36 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     // ---- per-voxel offsets / softmax of this head (as in the gather kernel)
     {
         const int p = lane & 7;
-        for (int v = tid >> 3; v < kTV; v += kTcThreads / 8) {
+        constexpr int kIter = kTV * 8 / kTcThreads;       // 4 voxels per 8-lane group
+        float2 off[kIter];
+        float lg[kIter];
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {              // all global loads in flight before any use
+            const int v = (tid >> 3) + it * (kTcThreads / 8);
             const int n = s_n[v];
-            if (n < 0 || s_bits[v] == 0) continue;
-            const float* row = logits + ((size_t)b * Nq + n) * ld;
-            float2 off = make_float2(0.f, 0.f);
-            float lg = -INFINITY;
-            if (p < NP) {
-                off = reinterpret_cast<const float2*>(row + h * NP * 2)[p];
-                lg = row[NH * NP * 2 + h * NP + p];
+            off[it] = make_float2(0.f, 0.f);
+            lg[it] = -INFINITY;
+            if (n >= 0 && s_bits[v] != 0 && p < NP) {
+                const float* row = logits + ((size_t)b * Nq + n) * ld;
+                off[it] = reinterpret_cast<const float2*>(row + h * NP * 2)[p];
+                lg[it] = row[NH * NP * 2 + h * NP + p];
             }
-            const unsigned gm = 0xffu << (lane & 24);
-            float m = lg;
-            m = fmaxf(m, __shfl_xor_sync(gm, m, 1));
-            m = fmaxf(m, __shfl_xor_sync(gm, m, 2));
-            m = fmaxf(m, __shfl_xor_sync(gm, m, 4));
-            const float e = (p < NP) ? expf(lg - m) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < kIter; ++it) {
+            const int v = (tid >> 3) + it * (kTcThreads / 8);
+            float m = lg[it];
+            m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 4));
+            const float e = (lg[it] > -INFINITY) ? expf(lg[it] - m) : 0.f;
             float s = e;
-            s += __shfl_xor_sync(gm, s, 1);
-            s += __shfl_xor_sync(gm, s, 2);
-            s += __shfl_xor_sync(gm, s, 4);
-            s_off[v * 16 + 2 * p] = off.x / (float)Sw;
-            s_off[v * 16 + 2 * p + 1] = off.y / (float)Sh;
-            s_aw[v * 8 + p] = e / s;
+            s += __shfl_xor_sync(VER_FULL_MASK, s, 1);
+            s += __shfl_xor_sync(VER_FULL_MASK, s, 2);
+            s += __shfl_xor_sync(VER_FULL_MASK, s, 4);
+            s_off[v * 16 + 2 * p] = off[it].x / (float)Sw;
+            s_off[v * 16 + 2 * p + 1] = off[it].y / (float)Sh;
+            s_aw[v * 8 + p] = s > 0.f ? e / s : 0.f;
         }
     }
     __syncthreads();
@@ -238,9 +245,9 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     for (uint32_t rest = cams; rest; rest &= rest - 1, ++k) {
         const int c = __ffs(rest) - 1;
         const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)c * B + b) * Nq;
-        const int cnt = s_cnt[c];
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
+            const int cnt = s_cnt[c * 2 + hf];
             __half* A = reinterpret_cast<__half*>(smem + (hf ? L.off_a1 : L.off_a0));
             if (k > 0) mbar_wait(&bar_mma[hf], (k - 1) & 1);      // previous camera's MMAs on this half retired
             if (hf == 1 && k > 0 && tid == 0) {
@@ -257,30 +264,29 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
             for (int i = tid; i < L.a_half_bytes / 16; i += kTcThreads)
                 reinterpret_cast<uint4*>(A)[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            // one thread per visible voxel of this half; entries are dealt round-robin to the warps
-            const int j = (tid & 31) * kTcWarps + (tid >> 5);
-            if (j < cnt) {
-                const int v = s_list[c * kTV + j];
-                if ((v >> 7) == hf) {
-                    const int r = v & 127;
-                    const float2 ref = rp[s_n[v]];
-                    for (int p = 0; p < NP; ++p) {
-                        const float aw = s_aw[v * 8 + p];
-                        const float x = (ref.x + s_off[v * 16 + 2 * p]) * (float)Sw - 0.5f;
-                        const float y = (ref.y + s_off[v * 16 + 2 * p + 1]) * (float)Sh - 0.5f;
-                        if (!(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
-                        const float xf = floorf(x), yf = floorf(y);
-                        const float fx = x - xf, fy = y - yf;
-                        const int x0 = (int)xf, y0 = (int)yf;
+            // one thread per (visible row, sampling point): 4 taps each; two points of a row may hit
+            // the same pixel, so the taps are accumulated with packed-half shared-memory atomics
+            for (int q = tid; q < cnt * 8; q += kTcThreads) {
+                const int p = q & 7;
+                if (p >= NP) continue;
+                const int r = s_list[(c * 2 + hf) * 128 + (q >> 3)];
+                const int v = hf * 128 + r;
+                const float2 ref = rp[s_n[v]];
+                const float aw = s_aw[v * 8 + p];
+                const float x = (ref.x + s_off[v * 16 + 2 * p]) * (float)Sw - 0.5f;
+                const float y = (ref.y + s_off[v * 16 + 2 * p + 1]) * (float)Sh - 0.5f;
+                if (!(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
+                const float xf = floorf(x), yf = floorf(y);
+                const float fx = x - xf, fy = y - yf;
+                const int x0 = (int)xf, y0 = (int)yf;
 #pragma unroll
-                        for (int cn = 0; cn < 4; ++cn) {
-                            const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
-                            if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
-                            const float wgt = aw * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
-                            __half* a = A + img_off(r, yi * Sw + xi, G);
-                            *a = __float2half_rn(__half2float(*a) + wgt);
-                        }
-                    }
+                for (int cn = 0; cn < 4; ++cn) {
+                    const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                    if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                    const float wgt = aw * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
+                    const int o = img_off(r, yi * Sw + xi, G);
+                    const __half hw = __float2half_rn(wgt), hz = __float2half(0.f);
+                    atomicAdd(reinterpret_cast<__half2*>(A + (o & ~1)), (o & 1) ? __halves2half2(hz, hw) : __halves2half2(hw, hz));
                 }
             }
             proxy_fence();                       // generic-proxy writes of A -> async proxy (tensor core)
@@ -618,7 +624,11 @@ int launch_bwd_tc(const __half* vimg, const float* logits, int ld, const float* 
 
 // ---- entry points used by sca.cu's dispatch (value_layout == VER_LAYOUT_TC_IMAGE) and the C ABI
 int ver_tc_supported(int Ncam, int S, int Dh, int NP) {
-    return Ncam <= kMaxCam && NP >= 1 && NP <= 8 && S <= 256 && (Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128);
+    if (!(Ncam <= kMaxCam && NP >= 1 && NP <= 8 && S <= 256 && (Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128)))
+        return 0;
+    const int SP = (S + 15) / 16 * 16;
+    return TcFwdSmem(Dh, SP).total + 2048 <= ver_device_max_smem_optin() &&
+           TcBwdSmem(Dh, SP).total + 2048 <= ver_device_max_smem_optin();
 }
 
 extern "C" int ver_value_image_f16(const void* value, void* vimg, int Bv, int S, int NH, int Dh,

@@ -52,6 +52,21 @@ class FFN(PrecisionMixin, BaseModule):
             identity = x
         return identity.to(out.dtype) + self.dropout_layer(out)
 
+    def forward_unfused_tail(self, x):
+        """Fast path used by VoxelFormerLayer when the FFN is followed by 'norm' (num_fcs == 2, ReLU):
+        returns (pre-dropout output of the last Linear, final dropout p) so that the caller can fuse
+        dropout + identity add + LayerNorm into one kernel; the inner ReLU + Dropout is one kernel too."""
+        from .. import ops
+        cd = self.compute_dtype or x.dtype
+        first, last, last_drop = self.layers[0], self.layers[1], self.layers[2]
+        a = self._linear(x, first[0], cd)
+        h = ops.relu_dropout_(a, first[2].p, self.training)
+        return self._linear(h, last, cd), last_drop.p
+
+    def fusable(self):
+        return (self.num_fcs == 2 and self.add_identity and isinstance(self.activate, nn.ReLU)
+                and isinstance(self.dropout_layer, nn.Identity))
+
 
 if not HAVE_MMCV:
     FEEDFORWARD_NETWORK.register_module()(FFN)

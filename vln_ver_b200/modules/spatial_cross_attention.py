@@ -125,6 +125,9 @@ class SpatialCrossAttention(PrecisionMixin, BaseModule):
         else:           # fp32 (parity mode) / unsupported shapes: shared-memory gather kernels
             slots = ops.sca_sample(v, logits, vis, Sh, Sw, da.num_heads, da.num_points, head_major=True)
         slots = self._linear(slots, self.output_proj, cd)
+        if kwargs.get('return_unfused', False):
+            # VoxelFormerLayer fuses dropout + residual + the following LayerNorm into one kernel
+            return slots, inp_residual
         return self.dropout(slots) + inp_residual.to(slots.dtype)
 
 

@@ -19,6 +19,7 @@ from ..registry import (TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, BaseModul
                         build_transformer_layer)
 from .custom_base_transformer_layer import MyCustomBaseTransformerLayer
 from .precision import PrecisionMixin
+from .spatial_cross_attention import SpatialCrossAttention
 
 
 def apply_layernorm(norm, x):
@@ -189,6 +190,7 @@ class VoxelFormerLayer(MyCustomBaseTransformerLayer):
                          ffn_dropout=ffn_dropout, operation_order=operation_order, act_cfg=act_cfg,
                          norm_cfg=norm_cfg, ffn_num_fcs=ffn_num_fcs, **kwargs)
         self.fp16_enabled = False
+        self.fuse_epilogues = True
 
     def forward(self, query, key=None, value=None, bev_pos=None, query_pos=None, key_pos=None,
                 attn_masks=None, query_key_padding_mask=None, key_padding_mask=None, ref_2d=None,
@@ -203,7 +205,39 @@ class VoxelFormerLayer(MyCustomBaseTransformerLayer):
             warnings.warn(f'Use same attn_mask in all attentions in {self.__class__.__name__} ')
         else:
             assert len(attn_masks) == self.num_attn
-        for layer in self.operation_order:
+        order = self.operation_order
+        skip_norm = False
+        for op_i, layer in enumerate(order):
+            # fused epilogue: [cross_attn|ffn] followed by 'norm' -> dropout + residual + LayerNorm in
+            # one kernel (ver_dropout_add_layernorm_*); same arithmetic as the separate steps below
+            fuse = (self.fuse_epilogues and not self.pre_norm and query.is_cuda
+                    and op_i + 1 < len(order) and order[op_i + 1] == 'norm'
+                    and query.shape[-1] % 8 == 0 and query.shape[-1] <= 1024)
+            if layer == 'norm' and skip_norm:
+                skip_norm = False
+                norm_index += 1
+                continue
+            if fuse and layer == 'cross_attn' and isinstance(self.attentions[attn_index], SpatialCrossAttention):
+                attn, norm = self.attentions[attn_index], self.norms[norm_index]
+                proj, resid = attn(
+                    query, key, value, None, query_pos=query_pos, key_pos=key_pos, reference_points=ref_3d,
+                    reference_points_cam=reference_points_cam, mask=mask, attn_mask=attn_masks[attn_index],
+                    key_padding_mask=key_padding_mask, spatial_shapes=spatial_shapes,
+                    level_start_index=level_start_index, return_unfused=True, **kwargs)
+                query = ops.dropout_add_layernorm(proj, resid.to(proj.dtype), norm.weight, norm.bias,
+                                                  attn.dropout.p, norm.eps, attn.training)
+                attn_index += 1
+                identity = query
+                skip_norm = True
+                continue
+            if fuse and layer == 'ffn' and getattr(self.ffns[ffn_index], 'fusable', lambda: False)():
+                ffn, norm = self.ffns[ffn_index], self.norms[norm_index]
+                out, p_last = ffn.forward_unfused_tail(query)
+                query = ops.dropout_add_layernorm(out, query.to(out.dtype), norm.weight, norm.bias, p_last,
+                                                  norm.eps, ffn.training)
+                ffn_index += 1
+                skip_norm = True
+                continue
             if layer == 'self_attn':
                 query = self.attentions[attn_index](
                     query, prev_bev, prev_bev, identity if self.pre_norm else None, query_pos=bev_pos,

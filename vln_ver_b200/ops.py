@@ -319,7 +319,13 @@ def sca_sample_tc(value, logits, vis, Sh, Sw, NH, NP):
 
 
 def tc_supported(dtype, Ncam, S, Dh, NP):
-    return dtype == torch.float16 and Ncam <= 32 and 1 <= NP <= 8 and S <= 256 and Dh in (32, 64, 96, 128)
+    """shapes the tcgen05 sampler covers (the rest takes the gather kernels); the shared-memory
+    budget of the forward kernel (2 value images + 2 interpolation-matrix halves) caps Dh at 96 for
+    14x14 maps."""
+    if not (dtype == torch.float16 and Ncam <= 32 and 1 <= NP <= 8 and S <= 256 and Dh in (32, 64, 96, 128)):
+        return False
+    SP = (S + 15) // 16 * 16
+    return 2 * Dh * SP * 2 + 2 * 128 * SP * 2 + 36 * 1024 <= 227 * 1024
 
 
 # ------------------------------------------------------------------ A8 prologue, A6 epilogue
@@ -349,6 +355,91 @@ def add_layernorm(x, residual, gamma, beta, eps=1e-5):
                                 _ptr(_c(beta.detach(), torch.float32)), _ptr(y), x.numel() // C, C,
                                 float(eps), _stream()))
     return y
+
+
+_SEED_COUNTER = [0]
+
+
+def _next_seed():
+    """A fresh 64-bit Philox key per dropout site and step, derived from torch's global seed."""
+    _SEED_COUNTER[0] += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _SEED_COUNTER[0] * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+
+
+class DropoutAddLayerNormFunction(Function):
+    """y = LayerNorm(residual + dropout(x)): one pass forward, one pass backward
+    (the 'norm' steps of VoxelFormerLayer fused with the residual adds / dropouts in front of them)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, p, eps, training):
+        _need_cuda(x, weight, bias)
+        x = _c(x)
+        r = _c(residual, x.dtype) if residual is not None else None
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        need_bwd = any(ctx.needs_input_grad[:4])
+        z = torch.empty_like(x) if need_bwd else None
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if need_bwd else None
+        p_eff = float(p) if training else 0.0
+        seed = _next_seed()
+        w32, b32 = _c(weight.detach(), torch.float32), _c(bias.detach(), torch.float32)
+        check(lib.ver_dropout_add_layernorm_fwd(_code(x.dtype), _ptr(x), _ptr(r), _ptr(w32), _ptr(b32), _ptr(y),
+                                                _ptr(z), _ptr(stats), rows, C, float(eps), p_eff, seed,
+                                                _stream()))
+        if need_bwd:
+            ctx.save_for_backward(z, stats, w32)
+            ctx.p, ctx.seed, ctx.has_res, ctx.wdtype = p_eff, seed, residual is not None, weight.dtype
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        z, stats, w32 = ctx.saved_tensors
+        C = z.shape[-1]
+        rows = z.numel() // C
+        dy = _c(dy, z.dtype)
+        dx = torch.empty_like(z)
+        dres = torch.empty_like(z) if ctx.has_res else None
+        nb = lib.ver_dropout_add_layernorm_bwd_blocks(rows)
+        dgp = torch.empty((nb, C), dtype=torch.float32, device=z.device)
+        dbp = torch.empty((nb, C), dtype=torch.float32, device=z.device)
+        check(lib.ver_dropout_add_layernorm_bwd(_code(z.dtype), _ptr(dy), _ptr(z), _ptr(stats), _ptr(w32),
+                                                _ptr(dx), _ptr(dres), _ptr(dgp), _ptr(dbp), rows, C, ctx.p,
+                                                ctx.seed, _stream()))
+        return dx, dres, dgp.sum(0).to(ctx.wdtype), dbp.sum(0).to(ctx.wdtype), None, None, None
+
+
+def dropout_add_layernorm(x, residual, weight, bias, p=0.0, eps=1e-5, training=False):
+    return DropoutAddLayerNormFunction.apply(x, residual, weight, bias, p, eps, training)
+
+
+class ReluDropoutFunction(Function):
+    """h = dropout(relu(a)) in place (mmcv FFN's Linear -> ReLU(inplace) -> Dropout)."""
+
+    @staticmethod
+    def forward(ctx, a, p, training):
+        _need_cuda(a)
+        assert a.is_contiguous() and a.numel() % 8 == 0
+        p_eff = float(p) if training else 0.0
+        check(lib.ver_relu_dropout_fwd(_code(a.dtype), _ptr(a), _ptr(a), a.numel(), p_eff, _next_seed(), _stream()))
+        ctx.mark_dirty(a)
+        ctx.save_for_backward(a)
+        ctx.p = p_eff
+        return a
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dh):
+        h, = ctx.saved_tensors
+        dh = _c(dh, h.dtype)
+        da = torch.empty_like(h)
+        check(lib.ver_relu_dropout_bwd(_code(h.dtype), _ptr(dh), _ptr(h), _ptr(da), h.numel(), ctx.p, _stream()))
+        return da, None, None
+
+
+def relu_dropout_(a, p=0.0, training=False):
+    return ReluDropoutFunction.apply(a, p, training)
 
 
 # ------------------------------------------------------------------ A11, A12
