@@ -185,6 +185,29 @@ def test_head_golden_and_decode_bit_exact():
         assert torch.equal(dec['occupancy_preds'].cpu(), c['decode']), 'decode index tensor must be bit-exact'
 
 
+def test_refine_occ_default_branch_tail_vs_oracle():
+    """shipped vocc.py head tail (HEAD:551-580): raw .view reinterpretations, 3x ConvTranspose3d
+    (library conv), column occ_proj -- against the restated oracle, small lateral grid."""
+    grid = (2, 3, 3)
+    cfg = V.vocc_head_cfg(*grid, num_cams=6, embed_dims=768, only_occ=False, refine_occ=True,
+                          occupancy_size=[0.5, 0.5, 0.5], occ_dims=16, num_layers=1, with_decoder=False)
+    torch.manual_seed(3)
+    head = V.build_head(cfg)
+    with torch.no_grad():
+        for p in head.up_sample.parameters():
+            p.mul_(0.5)
+    assert (head.occ_xdim, head.occ_ydim, head.occ_zdim) == (24, 24, 7)
+    bev = torch.randn(2, 18, 768)
+    sd = {k: v.detach() for k, v in head.state_dict().items()}
+    with torch.no_grad():
+        ref = ver_ref.occ_head(sd, '', bev, *grid, 24, 24, 7, occ_dims=16, refine_occ=True, only_occ=False)
+    head = head.to(DEV).eval()
+    with torch.no_grad():
+        y = head._occupancy_tail(cuda(bev), 2)
+    assert y.shape == (2, 7 * 24 * 24, 16)
+    assert rel_err(y, ref) < 1e-4       # three chained 768x768x75-tap library convolutions in fp32
+
+
 # ------------------------------------------------------------------ full lift+encode vs oracle
 def make_head(grid, ncam, C=768, seed=0, **kw):
     torch.manual_seed(seed)

@@ -105,6 +105,7 @@ __global__ void value_image_kernel(const __half* __restrict__ value, __half* __r
 // ---------------------------------------------------------------- forward
 constexpr int kTcThreads = 512;
 constexpr int kTcWarps = kTcThreads / 32;
+constexpr int kBuildWarps = kTcWarps - 1;   // warps 0..14 build A, warp 15 feeds the tensor cores
 constexpr int kTZ = 4, kTH = 8, kTW = 8;
 constexpr int kTV = kTZ * kTH * kTW;        // 256 voxel rows = two M=128 halves
 constexpr int kMaxCam = 32;
@@ -146,7 +147,7 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.off_bits);
     uint8_t* s_list = smem + L.off_list;
     int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
-    __shared__ __align__(8) uint64_t bar_v[2], bar_mma[2];
+    __shared__ __align__(8) uint64_t bar_v[2], bar_mma[2], bar_built[2];
     __shared__ uint32_t s_union, s_tmem;
 
     const int b = blockIdx.z, h = blockIdx.y;
@@ -160,6 +161,8 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
         mbar_init(&bar_v[1], 1);
         mbar_init(&bar_mma[0], 1);
         mbar_init(&bar_mma[1], 1);
+        mbar_init(&bar_built[0], kBuildWarps);
+        mbar_init(&bar_built[1], kBuildWarps);
         mbar_fence_init();
         s_union = 0;
     }
@@ -240,70 +243,101 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     __syncthreads();
 
     constexpr uint32_t idesc = umma_idesc(128, DH, 0, 0);
-    // ---- cameras in ascending order; two 128-row halves pipeline build (threads) against MMA (async)
+    // ---- cameras in ascending order.  Warp roles: warps 0..14 build the interpolation matrix (two
+    //      128-row halves, so building one half overlaps the tensor-core work on the other), warp 15
+    //      streams value images in (TMA) and issues the MMAs.  Hand-offs are mbarriers only:
+    //        bar_built[hf]  builders -> MMA warp   (one arrival per builder warp)
+    //        bar_mma[hf]    MMA retired (tcgen05.commit) -> builders may overwrite A[hf]; V buffer reuse
+    //        bar_v[buf]     value image landed
     int k = 0;
-    for (uint32_t rest = cams; rest; rest &= rest - 1, ++k) {
-        const int c = __ffs(rest) - 1;
-        const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)c * B + b) * Nq;
+    if (warp == kBuildWarps) {
+        if (lane == 0) {
+            for (uint32_t rest = cams; rest; rest &= rest - 1, ++k) {
+                for (int hf = 0; hf < 2; ++hf) {
+                    if (k > 0) mbar_wait(&bar_mma[hf], (k - 1) & 1);   // safe: phase k of this half not issued yet
+                    if (hf == 1 && k > 0) {
+                        // both halves of camera k-1 retired -> V buffer (k+1)&1 is free: prefetch camera k+1
+                        const uint32_t nxt = rest & (rest - 1);
+                        if (nxt) {
+                            const int cn = __ffs(nxt) - 1;
+                            mbar_expect_tx(&bar_v[(k + 1) & 1], L.v_bytes);
+                            bulk_g2s(smem + (((k + 1) & 1) ? L.off_v1 : L.off_v0),
+                                     vbase + (size_t)cn * v_stride_bv, L.v_bytes, &bar_v[(k + 1) & 1]);
+                        }
+                    }
+                    mbar_wait(&bar_built[hf], k & 1);
+                    tc_fence_after();
+                    if (hf == 0) mbar_wait(&bar_v[k & 1], (k >> 1) & 1);
+                    const uint32_t a_addr = smem_u32(smem + (hf ? L.off_a1 : L.off_a0));
+                    const uint32_t v_addr = smem_u32(smem + ((k & 1) ? L.off_v1 : L.off_v0));
+                    for (int ks = 0; ks < SP / 16; ++ks)
+                        umma_f16(tmem + hf * DH, umma_desc(a_addr + ks * 256, 128, G * 128),
+                                 umma_desc(v_addr + ks * 256, 128, G * 128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
+                    umma_commit(&bar_mma[hf]);
+                }
+            }
+        }
+        k = __popc(cams);
+    } else {
+        constexpr int kBT = kBuildWarps * 32;                  // 480 builder threads
+        constexpr int kRounds = (128 * 8 + kBT - 1) / kBT;     // (row, point) pairs of a half / builders
+        for (uint32_t rest = cams; rest; rest &= rest - 1, ++k) {
+            const int c = __ffs(rest) - 1;
+            const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)c * B + b) * Nq;
 #pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {
-            const int cnt = s_cnt[c * 2 + hf];
-            __half* A = reinterpret_cast<__half*>(smem + (hf ? L.off_a1 : L.off_a0));
-            if (k > 0) mbar_wait(&bar_mma[hf], (k - 1) & 1);      // previous camera's MMAs on this half retired
-            if (hf == 1 && k > 0 && tid == 0) {
-                // both halves of camera k-1 retired -> its V buffer ((k+1)&1) is free: prefetch camera k+1
-                const uint32_t nxt = rest & (rest - 1);
-                if (nxt) {
-                    const int cn = __ffs(nxt) - 1;
-                    mbar_expect_tx(&bar_v[(k + 1) & 1], L.v_bytes);
-                    bulk_g2s(smem + (((k + 1) & 1) ? L.off_v1 : L.off_v0), vbase + (size_t)cn * v_stride_bv,
-                             L.v_bytes, &bar_v[(k + 1) & 1]);
-                }
-            }
-            tc_fence_after();
-            for (int i = tid; i < L.a_half_bytes / 16; i += kTcThreads)
-                reinterpret_cast<uint4*>(A)[i] = make_uint4(0, 0, 0, 0);
-            __syncthreads();
-            // one thread per (visible row, sampling point): 4 taps each; two points of a row may hit
-            // the same pixel, so the taps are accumulated with packed-half shared-memory atomics
-            for (int q = tid; q < cnt * 8; q += kTcThreads) {
-                const int p = q & 7;
-                if (p >= NP) continue;
-                const int r = s_list[(c * 2 + hf) * 128 + (q >> 3)];
-                const int v = hf * 128 + r;
-                const float2 ref = rp[s_n[v]];
-                const float aw = s_aw[v * 8 + p];
-                const float x = (ref.x + s_off[v * 16 + 2 * p]) * (float)Sw - 0.5f;
-                const float y = (ref.y + s_off[v * 16 + 2 * p + 1]) * (float)Sh - 0.5f;
-                if (!(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
-                const float xf = floorf(x), yf = floorf(y);
-                const float fx = x - xf, fy = y - yf;
-                const int x0 = (int)xf, y0 = (int)yf;
+            for (int hf = 0; hf < 2; ++hf) {
+                const int cnt = s_cnt[c * 2 + hf];
+                __half* A = reinterpret_cast<__half*>(smem + (hf ? L.off_a1 : L.off_a0));
+                // reference points of "my" (row, point) pairs first: their L2 latency hides behind the
+                // wait / zeroing below
+                float2 ref[kRounds];
+                int row[kRounds];
 #pragma unroll
-                for (int cn = 0; cn < 4; ++cn) {
-                    const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
-                    if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
-                    const float wgt = aw * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
-                    const int o = img_off(r, yi * Sw + xi, G);
-                    const __half hw = __float2half_rn(wgt), hz = __float2half(0.f);
-                    atomicAdd(reinterpret_cast<__half2*>(A + (o & ~1)), (o & 1) ? __halves2half2(hz, hw) : __halves2half2(hw, hz));
+                for (int rr = 0; rr < kRounds; ++rr) {
+                    const int q = tid + rr * kBT;
+                    row[rr] = -1;
+                    if (q < cnt * 8 && (q & 7) < NP) {
+                        row[rr] = s_list[(c * 2 + hf) * 128 + (q >> 3)];
+                        ref[rr] = rp[s_n[hf * 128 + row[rr]]];
+                    }
                 }
-            }
-            proxy_fence();                       // generic-proxy writes of A -> async proxy (tensor core)
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                if (hf == 0) mbar_wait(&bar_v[k & 1], (k >> 1) & 1);          // this camera's V image landed
-                const uint32_t a_addr = smem_u32(A);
-                const uint32_t v_addr = smem_u32(smem + ((k & 1) ? L.off_v1 : L.off_v0));
-                for (int ks = 0; ks < SP / 16; ++ks)
-                    umma_f16(tmem + hf * DH, umma_desc(a_addr + ks * 256, 128, G * 128),
-                             umma_desc(v_addr + ks * 256, 128, G * 128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(&bar_mma[hf]);
+                if (k > 0) mbar_wait(&bar_mma[hf], (k - 1) & 1);  // previous camera's MMAs on this half retired
+                for (int i = tid; i < L.a_half_bytes / 16; i += kBT)
+                    reinterpret_cast<uint4*>(A)[i] = make_uint4(0, 0, 0, 0);
+                asm volatile("bar.sync 1, %0;" ::"n"(kBT) : "memory");
+                // one thread per (visible row, sampling point): 4 taps each; two points of a row may hit
+                // the same pixel, so the taps are accumulated with packed-half shared-memory atomics
+#pragma unroll
+                for (int rr = 0; rr < kRounds; ++rr) {
+                    if (row[rr] < 0) continue;
+                    const int p = tid & 7;                    // kBT % 8 == 0
+                    const int r = row[rr], v = hf * 128 + r;
+                    const float aw = s_aw[v * 8 + p];
+                    const float x = (ref[rr].x + s_off[v * 16 + 2 * p]) * (float)Sw - 0.5f;
+                    const float y = (ref[rr].y + s_off[v * 16 + 2 * p + 1]) * (float)Sh - 0.5f;
+                    if (!(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
+                    const float xf = floorf(x), yf = floorf(y);
+                    const float fx = x - xf, fy = y - yf;
+                    const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                        if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                        const float wgt = aw * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
+                        const int o = img_off(r, yi * Sw + xi, G);
+                        const __half hw = __float2half_rn(wgt), hz = __float2half(0.f);
+                        atomicAdd(reinterpret_cast<__half2*>(A + (o & ~1)),
+                                  (o & 1) ? __halves2half2(hz, hw) : __halves2half2(hw, hz));
+                    }
+                }
+                proxy_fence();                   // generic-proxy writes of A -> async proxy (tensor core)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_built[hf]);
             }
         }
     }
+    __syncwarp();
     // ---- epilogue: slots = sum / max(count, 1)
     if (cams) {
         mbar_wait(&bar_mma[0], (k - 1) & 1);
@@ -343,6 +377,7 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
 // ---------------------------------------------------------------- backward
 constexpr int kBtThreads = 256;
 constexpr int kHitsPerChunk = 128;
+constexpr int kRnd = kHitsPerChunk * 8 / kBtThreads;    // (hit, point) pairs per thread and chunk
 
 struct TcBwdSmem {
     int v_bytes, a_bytes, g_bytes;
@@ -421,57 +456,84 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
         if (tid < kHitsPerChunk) s_n[tid] = tid < rows ? idx[base + tid] : -1;
         __syncthreads();
         // ---- G image: gather grad_slots rows (16-byte chunks = 8 channels of one hit)
-        for (int i = tid; i < kHitsPerChunk * CG; i += kBtThreads) {
-            const int r = i / CG, cg = i % CG;
-            const int n = s_n[r];
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (n >= 0)
-                val = *reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH + cg * 8);
-            *reinterpret_cast<uint4*>(Gimg + ((r >> 3) * CG + cg) * 64 + (r & 7) * 8) = val;
+        {
+            constexpr int kG = (kHitsPerChunk * CG + kBtThreads - 1) / kBtThreads;
+            uint4 val[kG];
+#pragma unroll
+            for (int u = 0; u < kG; ++u) {                 // loads in flight together
+                const int i = tid + u * kBtThreads;
+                val[u] = make_uint4(0, 0, 0, 0);
+                if (i < kHitsPerChunk * CG) {
+                    const int n = s_n[i / CG];
+                    if (n >= 0)
+                        val[u] = *reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH +
+                                                                 (i % CG) * 8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kG; ++u) {
+                const int i = tid + u * kBtThreads;
+                if (i < kHitsPerChunk * CG) {
+                    const int r = i / CG, cg = i % CG;
+                    *reinterpret_cast<uint4*>(Gimg + ((r >> 3) * CG + cg) * 64 + (r & 7) * 8) = val[u];
+                }
+            }
         }
-        // ---- A' rows: thread per hit (threads 0..127)
-        float p_aw[8], p_x[8], p_y[8];
-        float inv_cnt = 0.f;
-        int my_n = -1;
-        if (tid < kHitsPerChunk) {
-            my_n = s_n[tid];
-            if (my_n >= 0) {
-                const int r = tid;
-                const float* row = logits + ((size_t)b * Nq + my_n) * ld;
-                float lg[8], mx = -INFINITY;
+        // ---- A' rows: one thread per (hit, point); the 8 lanes of a hit share the softmax via shuffles
+        float q_aw[kRnd], q_x[kRnd], q_y[kRnd], q_ic[kRnd];
+        int q_n[kRnd];
+        {
+            const int p = tid & 7;
+            float2 off[kRnd], ref[kRnd];
+            float lg[kRnd];
+            uint32_t vb[kRnd];
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    lg[p] = p < NP ? row[NH * NP * 2 + h * NP + p] : -INFINITY;
-                    mx = fmaxf(mx, lg[p]);
-                }
-                float sum = 0.f;
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    lg[p] = p < NP ? expf(lg[p] - mx) : 0.f;
-                    sum += lg[p];
-                }
-                const float2 ref = rp[my_n];
-                inv_cnt = 1.f / (float)max(__popc(vis_bits[(size_t)b * Nq + my_n]), 1);
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    float2 off = make_float2(0.f, 0.f);
-                    if (p < NP) off = reinterpret_cast<const float2*>(row + h * NP * 2)[p];
-                    p_aw[p] = lg[p] / sum;
-                    p_x[p] = (ref.x + off.x / (float)Sw) * (float)Sw - 0.5f;
-                    p_y[p] = (ref.y + off.y / (float)Sh) * (float)Sh - 0.5f;
-                    const float x = p_x[p], y = p_y[p];
-                    if (p >= NP || !(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
-                    const float xf = floorf(x), yf = floorf(y);
-                    const float fx = x - xf, fy = y - yf;
-                    const int x0 = (int)xf, y0 = (int)yf;
-#pragma unroll
-                    for (int cn = 0; cn < 4; ++cn) {
-                        const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
-                        if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
-                        const float wgt = inv_cnt * p_aw[p] * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
-                        __half* a = Aimg + img_off(r, yi * Sw + xi, G);
-                        *a = __float2half_rn(__half2float(*a) + wgt);
+            for (int rr = 0; rr < kRnd; ++rr) {           // all global loads first
+                const int n = s_n[(tid >> 3) + rr * (kBtThreads / 8)];
+                q_n[rr] = n;
+                off[rr] = ref[rr] = make_float2(0.f, 0.f);
+                lg[rr] = -INFINITY;
+                vb[rr] = 0;
+                if (n >= 0) {
+                    const float* row = logits + ((size_t)b * Nq + n) * ld;
+                    if (p < NP) {
+                        off[rr] = reinterpret_cast<const float2*>(row + h * NP * 2)[p];
+                        lg[rr] = row[NH * NP * 2 + h * NP + p];
                     }
+                    ref[rr] = rp[n];
+                    vb[rr] = vis_bits[(size_t)b * Nq + n];
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < kRnd; ++rr) {
+                const int r = (tid >> 3) + rr * (kBtThreads / 8);
+                float m = lg[rr];
+                m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 4));
+                const float e = lg[rr] > -INFINITY ? expf(lg[rr] - m) : 0.f;
+                float s = e;
+                s += __shfl_xor_sync(VER_FULL_MASK, s, 1);
+                s += __shfl_xor_sync(VER_FULL_MASK, s, 2);
+                s += __shfl_xor_sync(VER_FULL_MASK, s, 4);
+                q_aw[rr] = s > 0.f ? e / s : 0.f;
+                q_ic[rr] = 1.f / (float)max(__popc(vb[rr]), 1);
+                q_x[rr] = (ref[rr].x + off[rr].x / (float)Sw) * (float)Sw - 0.5f;
+                q_y[rr] = (ref[rr].y + off[rr].y / (float)Sh) * (float)Sh - 0.5f;
+                const float x = q_x[rr], y = q_y[rr];
+                if (q_n[rr] < 0 || p >= NP || !(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
+                const float xf = floorf(x), yf = floorf(y);
+                const float fx = x - xf, fy = y - yf;
+                const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+                for (int cn = 0; cn < 4; ++cn) {
+                    const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                    if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                    const float wgt = q_ic[rr] * q_aw[rr] * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
+                    const int o = img_off(r, yi * Sw + xi, G);
+                    const __half hw = __float2half_rn(wgt), hz = __float2half(0.f);
+                    atomicAdd(reinterpret_cast<__half2*>(Aimg + (o & ~1)),
+                              (o & 1) ? __halves2half2(hz, hw) : __halves2half2(hw, hz));
                 }
             }
         }
@@ -498,63 +560,65 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
         tc_fence_after();
         // ---- Dots: TMEM -> shared (fp32, two column halves through the retired A' buffer), then
         //      every hit thread picks its 32 taps
-        float ga[8], gx[8], gy[8];
+        float ga[kRnd], gx[kRnd], gy[kRnd];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) ga[p] = gx[p] = gy[p] = 0.f;
+        for (int rr = 0; rr < kRnd; ++rr) ga[rr] = gx[rr] = gy[rr] = 0.f;
         const int half_cols = ((SP / 2 + 15) / 16) * 16;         // 112 for SP = 208
         for (int part = 0; part < 2; ++part) {
             const int col0 = part * half_cols;
             const int ncols = min(half_cols, SP - col0);
-            if (warp < 4) {
-                for (int c0 = 0; c0 < ncols; c0 += 16) {
+            {   // all 8 warps dump: warp w reads TMEM lane quarter w & 3, column chunks split by w >> 2
+                const int hit = (warp & 3) * 32 + lane;
+                const int nch = ncols / 16, cbeg = (warp >> 2) ? (nch + 1) / 2 : 0,
+                          cend = (warp >> 2) ? nch : (nch + 1) / 2;
+                for (int ci = cbeg; ci < cend; ++ci) {
                     float vv[16];
-                    tmem_ld16(tm_dots + ((uint32_t)(warp * 32) << 16) + col0 + c0, vv);
-                    float4* d = reinterpret_cast<float4*>(dots + tid * half_cols + c0);
+                    tmem_ld16(tm_dots + ((uint32_t)((warp & 3) * 32) << 16) + col0 + ci * 16, vv);
+                    float4* d = reinterpret_cast<float4*>(dots + hit * half_cols + ci * 16);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) d[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
                 }
             }
             __syncthreads();
-            if (tid < kHitsPerChunk && my_n >= 0) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const float x = p_x[p], y = p_y[p];
-                    if (p >= NP || !(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
-                    const float xf = floorf(x), yf = floorf(y);
-                    const float fx = x - xf, fy = y - yf;
-                    const int x0 = (int)xf, y0 = (int)yf;
+            for (int rr = 0; rr < kRnd; ++rr) {
+                const float x = q_x[rr], y = q_y[rr];
+                if (q_n[rr] < 0 || (tid & 7) >= NP || !(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh))
+                    continue;
+                const int r = (tid >> 3) + rr * (kBtThreads / 8);
+                const float xf = floorf(x), yf = floorf(y);
+                const float fx = x - xf, fy = y - yf;
+                const int x0 = (int)xf, y0 = (int)yf;
 #pragma unroll
-                    for (int cn = 0; cn < 4; ++cn) {
-                        const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
-                        if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
-                        const int pix = yi * Sw + xi;
-                        if (pix < col0 || pix >= col0 + ncols) continue;
-                        const float d = dots[tid * half_cols + pix - col0];
-                        const float wx = (cn & 1) ? fx : 1.f - fx, wy = (cn >> 1) ? fy : 1.f - fy;
-                        ga[p] += wy * wx * d;
-                        gx[p] += ((cn & 1) ? wy : -wy) * d;
-                        gy[p] += ((cn >> 1) ? wx : -wx) * d;
-                    }
+                for (int cn = 0; cn < 4; ++cn) {
+                    const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                    if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                    const int pix = yi * Sw + xi;
+                    if (pix < col0 || pix >= col0 + ncols) continue;
+                    const float d = dots[r * half_cols + pix - col0];
+                    const float wx = (cn & 1) ? fx : 1.f - fx, wy = (cn >> 1) ? fy : 1.f - fy;
+                    ga[rr] += wy * wx * d;
+                    gx[rr] += ((cn & 1) ? wy : -wy) * d;
+                    gy[rr] += ((cn >> 1) ? wx : -wx) * d;
                 }
             }
             __syncthreads();
         }
-        // ---- softmax backward + accumulate into the per-voxel logit gradients
-        if (tid < kHitsPerChunk && my_n >= 0) {
-            float t = 0.f;
+        // ---- softmax backward (8-lane groups) + accumulate into the per-voxel logit gradients
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                ga[p] *= inv_cnt;
-                t += p_aw[p] * ga[p];
-            }
-            float* grow = glogits + ((size_t)b * Nq + my_n) * ld;
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                if (p >= NP) break;
-                atomicAdd(grow + NH * NP * 2 + h * NP + p, p_aw[p] * (ga[p] - t));
-                // d loc = aw * size * sum(...), d offset = d loc / size
-                atomicAdd(grow + h * NP * 2 + 2 * p, inv_cnt * p_aw[p] * (float)Sw * gx[p] / (float)Sw);
-                atomicAdd(grow + h * NP * 2 + 2 * p + 1, inv_cnt * p_aw[p] * (float)Sh * gy[p] / (float)Sh);
+        for (int rr = 0; rr < kRnd; ++rr) {
+            const float g = ga[rr] * q_ic[rr];
+            float t = q_aw[rr] * g;
+            t += __shfl_xor_sync(VER_FULL_MASK, t, 1);
+            t += __shfl_xor_sync(VER_FULL_MASK, t, 2);
+            t += __shfl_xor_sync(VER_FULL_MASK, t, 4);
+            const int p = tid & 7;
+            if (q_n[rr] >= 0 && p < NP) {
+                float* grow = glogits + ((size_t)b * Nq + q_n[rr]) * ld;
+                atomicAdd(grow + NH * NP * 2 + h * NP + p, q_aw[rr] * (g - t));
+                // d loc = aw * size * sum(...), d offset = d loc / size  -> the size cancels
+                atomicAdd(grow + h * NP * 2 + 2 * p, q_ic[rr] * q_aw[rr] * gx[rr]);
+                atomicAdd(grow + h * NP * 2 + 2 * p + 1, q_ic[rr] * q_aw[rr] * gy[rr]);
             }
         }
         tc_fence_before();
