@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Per-phase SM-clock breakdown of sca_fwd_tc_kernel (debug timers compiled into the kernel, enabled
+through the undocumented ver_debug_tc_timing hook).  Run on the GPU box:  python tools/tc_timing.py"""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vln_ver_b200 import _lib, ops, synth  # noqa: E402
+
+NAMES = {0: 'setup (barriers, tmem alloc, ids, lists)', 1: 'logits -> softmax/offsets', 2: 'B: refs + wait mma retire',
+         3: 'B: zero + bar.sync', 4: 'B: taps (atomics)', 5: 'B: fences + arrive', 6: 'B: drain', 7: 'epilogue',
+         8: 'M: prologue idle', 9: 'M: wait built', 10: 'M: wait V', 11: 'M: issue', 12: 'epilogue: wait last MMAs', 13: 'B: tap arithmetic',
+         16: 'bwd: zero A + ids', 17: 'bwd: G gather', 18: 'bwd: A rows', 19: 'bwd: fence+MMA', 20: 'bwd: dots dump+taps',
+         21: 'bwd: softmax bwd + atomics', 22: 'bwd: dV write'}
+
+
+def main():
+    B, ncam, grid, NH, Dh = 8, 18, (16, 40, 40), 8, 96
+    Nq = grid[0] * grid[1] * grid[2]
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=1235)
+    rpc, mask, bits, count = ops.point_sampling(torch.from_numpy(l2i).cuda(), torch.from_numpy(sh).cuda(),
+                                                synth.PC_RANGE, *grid)
+    vis = ops.Visibility(rpc, mask, bits, count, grid)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    value = (torch.randn(B * ncam, 196, NH * Dh, device='cuda', generator=g) * 0.5).half()
+    logits = torch.randn(B * Nq, 192, device='cuda', generator=g)
+    logits[:, :128] *= 2
+    fn = _lib.lib.ver_debug_tc_timing
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+    for _ in range(2):
+        ops.sca_sample_tc(value, logits, vis, 14, 14, NH, 8)
+    torch.cuda.synchronize()
+    assert fn(1, None) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.sca_sample_tc(value, logits, vis, 14, 14, NH, 8)
+    e1.record()
+    torch.cuda.synchronize()
+    out = (ctypes.c_ulonglong * 32)()
+    assert fn(0, out) == 0
+    ctas = (Nq // 256) * NH * B
+    print(f'launch {e0.elapsed_time(e1):.3f} ms (includes value_image), {ctas} CTAs, cycles per CTA:')
+    tot_b = sum(out[i] for i in range(8))
+    for i in range(14):
+        print(f'  [{i:2d}] {NAMES[i]:42s} {out[i] / ctas:10.0f}')
+    print(f'  builder thread total {tot_b / ctas:.0f} cycles/CTA')
+    # backward
+    v = value.clone().requires_grad_(True)
+    lg = logits.clone().requires_grad_(True)
+    o = ops.sca_sample_tc(v, lg, vis, 14, 14, NH, 8)
+    go = torch.randn_like(o)
+    o.backward(go, retain_graph=True)
+    torch.cuda.synchronize()
+    assert fn(1, None) == 0
+    e0.record()
+    o.backward(go)
+    e1.record()
+    torch.cuda.synchronize()
+    assert fn(0, out) == 0
+    bc = B * ncam * NH
+    print(f'backward {e0.elapsed_time(e1):.3f} ms (includes casts), {bc} CTAs, cycles per CTA:')
+    for i in range(16, 23):
+        print(f'  [{i:2d}] {NAMES[i]:42s} {out[i] / bc:10.0f}')
+
+
+if __name__ == '__main__':
+    main()

@@ -108,6 +108,24 @@ __device__ __forceinline__ void store_channels(float* dst, const float (&acc)[CP
         reinterpret_cast<float4*>(dst)[k] =
             make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
 }
+// 16-byte stores; dst must be 16-byte aligned and CPL a multiple of 8
+template <int CPL>
+__device__ __forceinline__ void store_channels16(__half* dst, const float (&acc)[CPL]) {
+#pragma unroll
+    for (int k = 0; k < CPL / 8; ++k) {
+        uint4 u;
+        __half2 h;
+        h = __floats2half2_rn(acc[8 * k], acc[8 * k + 1]);
+        u.x = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2half2_rn(acc[8 * k + 2], acc[8 * k + 3]);
+        u.y = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2half2_rn(acc[8 * k + 4], acc[8 * k + 5]);
+        u.z = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2half2_rn(acc[8 * k + 6], acc[8 * k + 7]);
+        u.w = *reinterpret_cast<const uint32_t*>(&h);
+        reinterpret_cast<uint4*>(dst)[k] = u;
+    }
+}
 template <int CPL>
 __device__ __forceinline__ void store_channels(__half* dst, const float (&acc)[CPL]) {
 #pragma unroll

@@ -102,6 +102,26 @@ __global__ void value_image_kernel(const __half* __restrict__ value, __half* __r
     }
 }
 
+// ---------------------------------------------------------------- phase timers (debug)
+// g_tc_timing[i] accumulates SM-clock deltas of phase i, written by ONE thread per role and CTA when
+// g_tc_timing_on != 0 (set through ver_debug_tc_timing); read back by tests/tools, never by the product.
+__device__ unsigned long long g_tc_timing[32];
+__device__ int g_tc_timing_on = 0;
+struct PhaseTimer {
+    bool on;
+    long long t;
+    __device__ __forceinline__ PhaseTimer(bool active) : on(active && g_tc_timing_on), t(0) {
+        if (on) t = clock64();
+    }
+    __device__ __forceinline__ void lap(int slot) {
+        if (on) {
+            const long long n = clock64();
+            atomicAdd(&g_tc_timing[slot], (unsigned long long)(n - t));
+            t = n;
+        }
+    }
+};
+
 // ---------------------------------------------------------------- forward
 constexpr int kTcThreads = 512;
 constexpr int kTcWarps = kTcThreads / 32;
@@ -113,7 +133,7 @@ constexpr int kMaxCam = 32;
 struct TcFwdSmem {
     // byte offsets inside dynamic shared memory
     int v_bytes, a_half_bytes;
-    int off_v0, off_v1, off_a0, off_a1, off_soff, off_saw, off_n, off_bits, off_list, off_cnt, total;
+    int off_v0, off_v1, off_a0, off_a1, off_soff, off_saw, off_n, off_bits, off_list, off_cnt, off_trash, total;
     __host__ __device__ TcFwdSmem(int Dh, int SP) {
         v_bytes = Dh * SP * 2;
         a_half_bytes = 128 * SP * 2;
@@ -127,7 +147,8 @@ struct TcFwdSmem {
         off_bits = off_n + kTV * 4;
         off_list = off_bits + kTV * 4;
         off_cnt = off_list + kMaxCam * kTV;
-        total = off_cnt + 2 * kMaxCam * 4;
+        off_trash = off_cnt + 2 * kMaxCam * 4;     // one fp16 sink per thread for out-of-map taps
+        total = off_trash + kTcThreads * 2;
     }
 };
 
@@ -156,6 +177,25 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h,
               tz = blockIdx.x / (tiles_w * tiles_h);
 
+    PhaseTimer tm(tid == 0), tm_mma(tid == kBuildWarps * 32);
+    // The offset / attention-logit rows of "my" voxels do not depend on anything computed below: issue
+    // the global loads first so that their latency overlaps barrier init, TMEM allocation and the
+    // visibility-list construction.
+    constexpr int kIter = kTV * 8 / kTcThreads;           // 4 voxels per 8-lane group
+    float2 off[kIter];
+    float lg[kIter];
+#pragma unroll
+    for (int it = 0; it < kIter; ++it) {
+        const int v = (tid >> 3) + it * (kTcThreads / 8);
+        const int w = tw * kTW + (v % kTW), hh = th * kTH + (v / kTW) % kTH, z = tz * kTZ + v / (kTW * kTH);
+        off[it] = make_float2(0.f, 0.f);
+        lg[it] = -INFINITY;
+        if (w < W && hh < H && z < Z && (lane & 7) < NP) {
+            const float* row = logits + ((size_t)b * Nq + (z * H + hh) * W + w) * ld;
+            off[it] = reinterpret_cast<const float2*>(row + h * NP * 2)[lane & 7];
+            lg[it] = row[NH * NP * 2 + h * NP + (lane & 7)];
+        }
+    }
     if (tid == 0) {
         mbar_init(&bar_v[0], 1);
         mbar_init(&bar_v[1], 1);
@@ -192,6 +232,7 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     }
     __syncthreads();
     const uint32_t cams = s_union;
+    tm.lap(0);                                   // setup: barriers, TMEM alloc, voxel ids + lists
     const size_t v_stride_bv = (size_t)NH * DH * SP;         // halves per view
     const __half* vbase = vimg + (size_t)b * Ncam * v_stride_bv + (size_t)h * DH * SP;
     if (tid == 0 && cams) {                                  // first two camera maps start streaming in
@@ -205,24 +246,9 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
             bulk_g2s(smem + L.off_v1, vbase + (size_t)c1 * v_stride_bv, L.v_bytes, &bar_v[1]);
         }
     }
-    // ---- per-voxel offsets / softmax of this head (as in the gather kernel)
+    // ---- per-voxel offsets / softmax of this head (loads were issued at kernel entry)
     {
         const int p = lane & 7;
-        constexpr int kIter = kTV * 8 / kTcThreads;       // 4 voxels per 8-lane group
-        float2 off[kIter];
-        float lg[kIter];
-#pragma unroll
-        for (int it = 0; it < kIter; ++it) {              // all global loads in flight before any use
-            const int v = (tid >> 3) + it * (kTcThreads / 8);
-            const int n = s_n[v];
-            off[it] = make_float2(0.f, 0.f);
-            lg[it] = -INFINITY;
-            if (n >= 0 && s_bits[v] != 0 && p < NP) {
-                const float* row = logits + ((size_t)b * Nq + n) * ld;
-                off[it] = reinterpret_cast<const float2*>(row + h * NP * 2)[p];
-                lg[it] = row[NH * NP * 2 + h * NP + p];
-            }
-        }
 #pragma unroll
         for (int it = 0; it < kIter; ++it) {
             const int v = (tid >> 3) + it * (kTcThreads / 8);
@@ -242,6 +268,8 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     }
     __syncthreads();
 
+    tm.lap(1);                                   // logits -> offsets / softmax
+    tm_mma.lap(8);
     constexpr uint32_t idesc = umma_idesc(128, DH, 0, 0);
     // ---- cameras in ascending order.  Warp roles: warps 0..14 build the interpolation matrix (two
     //      128-row halves, so building one half overlaps the tensor-core work on the other), warp 15
@@ -266,14 +294,17 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
                         }
                     }
                     mbar_wait(&bar_built[hf], k & 1);
+                    tm_mma.lap(9);                       // MMA warp: waiting for builders
                     tc_fence_after();
                     if (hf == 0) mbar_wait(&bar_v[k & 1], (k >> 1) & 1);
+                    tm_mma.lap(10);                      // MMA warp: waiting for the value image
                     const uint32_t a_addr = smem_u32(smem + (hf ? L.off_a1 : L.off_a0));
                     const uint32_t v_addr = smem_u32(smem + ((k & 1) ? L.off_v1 : L.off_v0));
                     for (int ks = 0; ks < SP / 16; ++ks)
                         umma_f16(tmem + hf * DH, umma_desc(a_addr + ks * 256, 128, G * 128),
                                  umma_desc(v_addr + ks * 256, 128, G * 128), idesc, (k > 0 || ks > 0) ? 1u : 0u);
                     umma_commit(&bar_mma[hf]);
+                    tm_mma.lap(11);                      // MMA warp: issuing
                 }
             }
         }
@@ -281,75 +312,126 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     } else {
         constexpr int kBT = kBuildWarps * 32;                  // 480 builder threads
         constexpr int kRounds = (128 * 8 + kBT - 1) / kBT;     // (row, point) pairs of a half / builders
+        const int p = tid & 7;                                 // kBT % 8 == 0: my sampling point
+        // my (row, reference point) pairs of one (camera, half); loaded ONE ITERATION AHEAD so the
+        // L2/HBM latency of reference_points_cam hides behind the previous half's work
+        auto prefetch = [&](int c, int hf, float2 (&rf)[kRounds], int (&rw)[kRounds]) {
+            const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)c * B + b) * Nq;
+            const int cnt = s_cnt[c * 2 + hf];
+#pragma unroll
+            for (int rr = 0; rr < kRounds; ++rr) {
+                const int q = tid + rr * kBT;
+                rw[rr] = -1;
+                if (q < cnt * 8 && p < NP) {
+                    rw[rr] = s_list[(c * 2 + hf) * 128 + (q >> 3)];
+                    rf[rr] = rp[s_n[hf * 128 + rw[rr]]];
+                }
+            }
+        };
+        float2 ref[kRounds];
+        int row[kRounds];
+#pragma unroll
+        for (int rr = 0; rr < kRounds; ++rr) row[rr] = -1;
+        if (cams) prefetch(__ffs(cams) - 1, 0, ref, row);
         for (uint32_t rest = cams; rest; rest &= rest - 1, ++k) {
             const int c = __ffs(rest) - 1;
-            const float2* rp = reinterpret_cast<const float2*>(rpc) + ((size_t)c * B + b) * Nq;
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
-                const int cnt = s_cnt[c * 2 + hf];
                 __half* A = reinterpret_cast<__half*>(smem + (hf ? L.off_a1 : L.off_a0));
-                // reference points of "my" (row, point) pairs first: their L2 latency hides behind the
-                // wait / zeroing below
-                float2 ref[kRounds];
-                int row[kRounds];
+                const int trash_rel = (int)(reinterpret_cast<__half*>(smem + L.off_trash) - A) + tid;
+                float2 nref[kRounds];
+                int nrow[kRounds];
 #pragma unroll
-                for (int rr = 0; rr < kRounds; ++rr) {
-                    const int q = tid + rr * kBT;
-                    row[rr] = -1;
-                    if (q < cnt * 8 && (q & 7) < NP) {
-                        row[rr] = s_list[(c * 2 + hf) * 128 + (q >> 3)];
-                        ref[rr] = rp[s_n[hf * 128 + row[rr]]];
-                    }
+                for (int rr = 0; rr < kRounds; ++rr) nrow[rr] = -1;
+                if (hf == 0) {
+                    prefetch(c, 1, nref, nrow);
+                } else {
+                    const uint32_t nxt = rest & (rest - 1);
+                    if (nxt) prefetch(__ffs(nxt) - 1, 0, nref, nrow);
                 }
                 if (k > 0) mbar_wait(&bar_mma[hf], (k - 1) & 1);  // previous camera's MMAs on this half retired
+                tm.lap(2);                               // builders: prefetch issue + wait for MMA retire
                 for (int i = tid; i < L.a_half_bytes / 16; i += kBT)
                     reinterpret_cast<uint4*>(A)[i] = make_uint4(0, 0, 0, 0);
                 asm volatile("bar.sync 1, %0;" ::"n"(kBT) : "memory");
-                // one thread per (visible row, sampling point): 4 taps each; two points of a row may hit
-                // the same pixel, so the taps are accumulated with packed-half shared-memory atomics
+                tm.lap(3);                               // builders: zero + barrier
+                // ---- taps of my (row, point) pairs: 4 bilinear corners each
+                int toff[kRounds][4];
+                float twgt[kRounds][4];
 #pragma unroll
                 for (int rr = 0; rr < kRounds; ++rr) {
-                    if (row[rr] < 0) continue;
-                    const int p = tid & 7;                    // kBT % 8 == 0
-                    const int r = row[rr], v = hf * 128 + r;
-                    const float aw = s_aw[v * 8 + p];
-                    const float x = (ref[rr].x + s_off[v * 16 + 2 * p]) * (float)Sw - 0.5f;
-                    const float y = (ref[rr].y + s_off[v * 16 + 2 * p + 1]) * (float)Sh - 0.5f;
-                    if (!(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
-                    const float xf = floorf(x), yf = floorf(y);
-                    const float fx = x - xf, fy = y - yf;
-                    const int x0 = (int)xf, y0 = (int)yf;
 #pragma unroll
-                    for (int cn = 0; cn < 4; ++cn) {
-                        const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
-                        if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
-                        const float wgt = aw * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
-                        const int o = img_off(r, yi * Sw + xi, G);
-                        const __half hw = __float2half_rn(wgt), hz = __float2half(0.f);
-                        atomicAdd(reinterpret_cast<__half2*>(A + (o & ~1)),
-                                  (o & 1) ? __halves2half2(hz, hw) : __halves2half2(hw, hz));
+                    for (int cn = 0; cn < 4; ++cn) {           // out-of-map taps: weight 0 into my private sink
+                        toff[rr][cn] = trash_rel;
+                        twgt[rr][cn] = 0.f;
+                    }
+                    if (row[rr] >= 0) {
+                        const int r = row[rr], v = hf * 128 + r;
+                        const float aw = s_aw[v * 8 + p];
+                        const float x = (ref[rr].x + s_off[v * 16 + 2 * p]) * (float)Sw - 0.5f;
+                        const float y = (ref[rr].y + s_off[v * 16 + 2 * p + 1]) * (float)Sh - 0.5f;
+                        if (x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh) {
+                            const float xf = floorf(x), yf = floorf(y);
+                            const float fx = x - xf, fy = y - yf;
+                            const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+                            for (int cn = 0; cn < 4; ++cn) {
+                                const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                                if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                                twgt[rr][cn] = aw * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
+                                toff[rr][cn] = img_off(r, yi * Sw + xi, G);
+                            }
+                        }
                     }
                 }
+                tm.lap(13);                              // builders: tap arithmetic (incl. exposed ref latency)
+                // ---- commit.  Two points of a row may hit the same pixel, so the 8 points of a row (8 lanes
+                // of one warp) write one after the other: plain read-modify-writes, deterministic, no atomics.
+                // Pairs of different rounds belong to different rows and never collide.
+#pragma unroll
+                for (int rr = 0; rr < kRounds; ++rr) {
+                    if (!__any_sync(VER_FULL_MASK, row[rr] >= 0)) continue;   // no pair of this warp in the round
+#pragma unroll
+                    for (int step = 0; step < 8; ++step) {
+                        if (p == step) {
+                            float old[4];                       // branch-free: 4 loads in flight, then 4 stores
+#pragma unroll
+                            for (int cn = 0; cn < 4; ++cn) old[cn] = __half2float(A[toff[rr][cn]]);
+#pragma unroll
+                            for (int cn = 0; cn < 4; ++cn) A[toff[rr][cn]] = __float2half_rn(old[cn] + twgt[rr][cn]);
+                        }
+                        __syncwarp();
+                    }
+                }
+                tm.lap(4);                               // builders: commit
                 proxy_fence();                   // generic-proxy writes of A -> async proxy (tensor core)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_built[hf]);
+                tm.lap(5);                               // builders: fences + arrive
+#pragma unroll
+                for (int rr = 0; rr < kRounds; ++rr) {
+                    ref[rr] = nref[rr];
+                    row[rr] = nrow[rr];
+                }
             }
         }
     }
     __syncwarp();
+    tm.lap(6);
     // ---- epilogue: slots = sum / max(count, 1)
     if (cams) {
         mbar_wait(&bar_mma[0], (k - 1) & 1);
         mbar_wait(&bar_mma[1], (k - 1) & 1);
     }
     tc_fence_after();
+    tm.lap(12);                                  // epilogue: wait for the last MMAs
     {
         const int q = warp & 3, grp = warp >> 2;          // TMEM lane quarter, column group
         const int hf = grp >> 1, cpart = grp & 1;         // 4 groups = 2 halves x 2 channel halves
         const int v = hf * 128 + q * 32 + lane;
         const int n = s_n[v];
-        const float inv_is_div = (float)max(__popc(s_bits[v]), 1);
+        const float inv_cnt = 1.f / (float)max(__popc(s_bits[v]), 1);   // fp16 output: reciprocal multiply
         constexpr int CH = DH / 2;                        // channels per thread
         __half* dst = (n >= 0) ? slots + ((size_t)b * Nq + n) * NH * DH + h * DH + cpart * CH : nullptr;
 #pragma unroll
@@ -364,13 +446,14 @@ sca_fwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
             if (dst) {
                 float o[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = vv[i] / inv_is_div;
-                store_channels<16>(dst + c0, o);
+                for (int i = 0; i < 16; ++i) o[i] = vv[i] * inv_cnt;
+                store_channels16<16>(dst + c0, o);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    tm.lap(7);                                   // epilogue: wait last MMAs, TMEM -> slots
     if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
@@ -381,7 +464,7 @@ constexpr int kRnd = kHitsPerChunk * 8 / kBtThreads;    // (hit, point) pairs pe
 
 struct TcBwdSmem {
     int v_bytes, a_bytes, g_bytes;
-    int off_v, off_a, off_g, off_n, total;
+    int off_v, off_a, off_g, off_n, off_trash, total;
     __host__ __device__ TcBwdSmem(int Dh, int SP) {
         v_bytes = Dh * SP * 2;
         a_bytes = kHitsPerChunk * SP * 2;               // also reused as the fp32 Dots staging buffer
@@ -389,8 +472,14 @@ struct TcBwdSmem {
         off_v = 0;
         off_a = off_v + v_bytes;
         off_g = off_a + a_bytes;
-        off_n = off_g + g_bytes;
-        total = off_n + kHitsPerChunk * 4;
+        // the fp32 Dots staging buffer (128 rows x dstride words) overlays A' and G once they are dead
+        const int half_cols = ((SP / 2 + 15) / 16) * 16;
+        const int dstride = half_cols + ((36 - (half_cols & 31)) & 31);
+        const int dots_bytes = kHitsPerChunk * dstride * 4;
+        const int ag = a_bytes + g_bytes;
+        off_n = off_a + (ag > dots_bytes ? ag : dots_bytes);
+        off_trash = off_n + kHitsPerChunk * 4;
+        total = off_trash + kBtThreads * 2;
     }
 };
 
@@ -434,6 +523,7 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
     const uint32_t tmem = s_tmem;
     const uint32_t tm_dv = tmem;                  // dV^T : lanes = channel, columns [0, SP) = pixel
     const uint32_t tm_dots = tmem + 256;          // Dots : lanes = hit,     columns [0, SP) = pixel
+    PhaseTimer tb(tid == 0);
     if (tid == 0) {
         mbar_expect_tx(&bar_v, L.v_bytes);
         bulk_g2s(smem + L.off_v, vimg + ((size_t)bv * NH + h) * DH * SP, L.v_bytes, &bar_v);
@@ -447,39 +537,34 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
 
     uint32_t phase = 0;
     const int nchunks = (nitems + kHitsPerChunk - 1) / kHitsPerChunk;
+    int next_n = (tid < kHitsPerChunk && tid < nitems) ? idx[tid] : -1;
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int base = chunk * kHitsPerChunk;
         const int rows = min(kHitsPerChunk, nitems - base);
         // ---- zero A', publish the chunk's voxel ids
         for (int i = tid; i < L.a_bytes / 16; i += kBtThreads)
             reinterpret_cast<uint4*>(Aimg)[i] = make_uint4(0, 0, 0, 0);
-        if (tid < kHitsPerChunk) s_n[tid] = tid < rows ? idx[base + tid] : -1;
+        if (tid < kHitsPerChunk) s_n[tid] = tid < rows ? next_n : -1;
+        // hit ids of the NEXT chunk: in flight during this chunk's work
+        if (tid < kHitsPerChunk && base + kHitsPerChunk + tid < nitems) next_n = idx[base + kHitsPerChunk + tid];
         __syncthreads();
-        // ---- G image: gather grad_slots rows (16-byte chunks = 8 channels of one hit)
-        {
-            constexpr int kG = (kHitsPerChunk * CG + kBtThreads - 1) / kBtThreads;
-            uint4 val[kG];
+        tb.lap(16);                                  // zero A' + hit ids
+        // ---- build.  G image: every thread first puts its 16-byte gathers of the hits' grad_slots rows in
+        //      flight; A' rows: one thread per (hit, point), the 8 lanes of a hit share the softmax via
+        //      shuffles; the G stores come last, when the loads have landed behind the A' work.
+        constexpr int kG = (kHitsPerChunk * CG + kBtThreads - 1) / kBtThreads;
+        uint4 gval[kG];
 #pragma unroll
-            for (int u = 0; u < kG; ++u) {                 // loads in flight together
-                const int i = tid + u * kBtThreads;
-                val[u] = make_uint4(0, 0, 0, 0);
-                if (i < kHitsPerChunk * CG) {
-                    const int n = s_n[i / CG];
-                    if (n >= 0)
-                        val[u] = *reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH +
-                                                                 (i % CG) * 8);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kG; ++u) {
-                const int i = tid + u * kBtThreads;
-                if (i < kHitsPerChunk * CG) {
-                    const int r = i / CG, cg = i % CG;
-                    *reinterpret_cast<uint4*>(Gimg + ((r >> 3) * CG + cg) * 64 + (r & 7) * 8) = val[u];
-                }
+        for (int u = 0; u < kG; ++u) {
+            const int i = tid + u * kBtThreads;
+            gval[u] = make_uint4(0, 0, 0, 0);
+            if (i < kHitsPerChunk * CG) {
+                const int n = s_n[i / CG];
+                if (n >= 0)
+                    gval[u] = *reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH +
+                                                              (i % CG) * 8);
             }
         }
-        // ---- A' rows: one thread per (hit, point); the 8 lanes of a hit share the softmax via shuffles
         float q_aw[kRnd], q_x[kRnd], q_y[kRnd], q_ic[kRnd];
         int q_n[kRnd];
         {
@@ -504,6 +589,9 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
                     vb[rr] = vis_bits[(size_t)b * Nq + n];
                 }
             }
+            int toff[kRnd][4];
+            float twgt[kRnd][4];
+            const int trash_rel = (int)(reinterpret_cast<__half*>(smem + L.off_trash) - Aimg) + tid;
 #pragma unroll
             for (int rr = 0; rr < kRnd; ++rr) {
                 const int r = (tid >> 3) + rr * (kBtThreads / 8);
@@ -512,31 +600,61 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
                 m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 2));
                 m = fmaxf(m, __shfl_xor_sync(VER_FULL_MASK, m, 4));
                 const float e = lg[rr] > -INFINITY ? expf(lg[rr] - m) : 0.f;
-                float s = e;
-                s += __shfl_xor_sync(VER_FULL_MASK, s, 1);
-                s += __shfl_xor_sync(VER_FULL_MASK, s, 2);
-                s += __shfl_xor_sync(VER_FULL_MASK, s, 4);
-                q_aw[rr] = s > 0.f ? e / s : 0.f;
+                float sm = e;
+                sm += __shfl_xor_sync(VER_FULL_MASK, sm, 1);
+                sm += __shfl_xor_sync(VER_FULL_MASK, sm, 2);
+                sm += __shfl_xor_sync(VER_FULL_MASK, sm, 4);
+                q_aw[rr] = sm > 0.f ? e / sm : 0.f;
                 q_ic[rr] = 1.f / (float)max(__popc(vb[rr]), 1);
                 q_x[rr] = (ref[rr].x + off[rr].x / (float)Sw) * (float)Sw - 0.5f;
                 q_y[rr] = (ref[rr].y + off[rr].y / (float)Sh) * (float)Sh - 0.5f;
                 const float x = q_x[rr], y = q_y[rr];
-                if (q_n[rr] < 0 || p >= NP || !(x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh)) continue;
-                const float xf = floorf(x), yf = floorf(y);
-                const float fx = x - xf, fy = y - yf;
-                const int x0 = (int)xf, y0 = (int)yf;
 #pragma unroll
                 for (int cn = 0; cn < 4; ++cn) {
-                    const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
-                    if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
-                    const float wgt = q_ic[rr] * q_aw[rr] * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
-                    const int o = img_off(r, yi * Sw + xi, G);
-                    const __half hw = __float2half_rn(wgt), hz = __float2half(0.f);
-                    atomicAdd(reinterpret_cast<__half2*>(Aimg + (o & ~1)),
-                              (o & 1) ? __halves2half2(hz, hw) : __halves2half2(hw, hz));
+                    toff[rr][cn] = trash_rel;
+                    twgt[rr][cn] = 0.f;
+                }
+                if (q_n[rr] >= 0 && p < NP && x > -1.f && y > -1.f && x < (float)Sw && y < (float)Sh) {
+                    const float xf = floorf(x), yf = floorf(y);
+                    const float fx = x - xf, fy = y - yf;
+                    const int x0 = (int)xf, y0 = (int)yf;
+#pragma unroll
+                    for (int cn = 0; cn < 4; ++cn) {
+                        const int xi = x0 + (cn & 1), yi = y0 + (cn >> 1);
+                        if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
+                        twgt[rr][cn] = q_ic[rr] * q_aw[rr] * (((cn >> 1) ? fy : 1.f - fy) * ((cn & 1) ? fx : 1.f - fx));
+                        toff[rr][cn] = img_off(r, yi * Sw + xi, G);
+                    }
                 }
             }
+            // the 8 points of a hit (8 lanes of one warp) commit their taps one after the other; the
+            // pairs a thread holds from different rounds belong to different hits and never collide
+#pragma unroll
+            for (int step = 0; step < 8; ++step) {
+                if (p == step) {
+                    float old[kRnd][4];
+#pragma unroll
+                    for (int rr = 0; rr < kRnd; ++rr)
+#pragma unroll
+                        for (int cn = 0; cn < 4; ++cn) old[rr][cn] = __half2float(Aimg[toff[rr][cn]]);
+#pragma unroll
+                    for (int rr = 0; rr < kRnd; ++rr)
+#pragma unroll
+                        for (int cn = 0; cn < 4; ++cn) Aimg[toff[rr][cn]] = __float2half_rn(old[rr][cn] + twgt[rr][cn]);
+                }
+                __syncwarp();
+            }
         }
+        tb.lap(18);                                  // A' rows (+ latency of the G gathers)
+#pragma unroll
+        for (int u = 0; u < kG; ++u) {
+            const int i = tid + u * kBtThreads;
+            if (i < kHitsPerChunk * CG) {
+                const int r = i / CG, cg = i % CG;
+                *reinterpret_cast<uint4*>(Gimg + ((r >> 3) * CG + cg) * 64 + (r & 7) * 8) = gval[u];
+            }
+        }
+        tb.lap(17);                                  // G image stores
         proxy_fence();
         tc_fence_before();
         __syncthreads();
@@ -558,12 +676,16 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
         mbar_wait(&bar_mma, phase);
         phase ^= 1;
         tc_fence_after();
-        // ---- Dots: TMEM -> shared (fp32, two column halves through the retired A' buffer), then
-        //      every hit thread picks its 32 taps
+        tb.lap(19);                                  // fences, MMA issue, MMA execution
+        // ---- Dots: TMEM -> shared (fp32, two column halves through the retired A'/G buffers), then
+        //      every hit thread picks the 32 taps of its row
         float ga[kRnd], gx[kRnd], gy[kRnd];
 #pragma unroll
         for (int rr = 0; rr < kRnd; ++rr) ga[rr] = gx[rr] = gy[rr] = 0.f;
         const int half_cols = ((SP / 2 + 15) / 16) * 16;         // 112 for SP = 208
+        // row stride of the fp32 staging buffer: == 4 (mod 32) words, so the 16-byte row stores of 8
+        // consecutive hits fall in 8 different bank groups (112 would be a 16-way conflict)
+        const int dstride = half_cols + ((36 - (half_cols & 31)) & 31);
         for (int part = 0; part < 2; ++part) {
             const int col0 = part * half_cols;
             const int ncols = min(half_cols, SP - col0);
@@ -574,7 +696,7 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
                 for (int ci = cbeg; ci < cend; ++ci) {
                     float vv[16];
                     tmem_ld16(tm_dots + ((uint32_t)((warp & 3) * 32) << 16) + col0 + ci * 16, vv);
-                    float4* d = reinterpret_cast<float4*>(dots + hit * half_cols + ci * 16);
+                    float4* d = reinterpret_cast<float4*>(dots + hit * dstride + ci * 16);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) d[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
                 }
@@ -595,7 +717,7 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
                     if (xi < 0 || xi >= Sw || yi < 0 || yi >= Sh) continue;
                     const int pix = yi * Sw + xi;
                     if (pix < col0 || pix >= col0 + ncols) continue;
-                    const float d = dots[r * half_cols + pix - col0];
+                    const float d = dots[r * dstride + pix - col0];
                     const float wx = (cn & 1) ? fx : 1.f - fx, wy = (cn >> 1) ? fy : 1.f - fy;
                     ga[rr] += wy * wx * d;
                     gx[rr] += ((cn & 1) ? wy : -wy) * d;
@@ -604,6 +726,7 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
             }
             __syncthreads();
         }
+        tb.lap(20);                                  // Dots: TMEM -> smem -> taps
         // ---- softmax backward (8-lane groups) + accumulate into the per-voxel logit gradients
 #pragma unroll
         for (int rr = 0; rr < kRnd; ++rr) {
@@ -624,6 +747,7 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
         tc_fence_before();
         __syncthreads();           // A'/dots and G buffers are free for the next chunk
         tc_fence_after();
+        tb.lap(21);                                  // softmax backward + atomics
     }
     // ---- grad_value: dV^T (TMEM lanes = channel) -> [bv][pix][h][ch] fp32
     if (nchunks == 0 && tid == 0) mbar_wait(&bar_v, 0);       // never leave a bulk copy in flight
@@ -645,6 +769,7 @@ sca_bwd_tc_kernel(const __half* __restrict__ vimg, const float* __restrict__ log
             }
         }
     }
+    tb.lap(22);                                  // dV^T -> grad_value
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512);
@@ -687,6 +812,14 @@ int launch_bwd_tc(const __half* vimg, const float* logits, int ld, const float* 
 }  // namespace
 
 // ---- entry points used by sca.cu's dispatch (value_layout == VER_LAYOUT_TC_IMAGE) and the C ABI
+extern "C" int ver_debug_tc_timing(int enable, unsigned long long* host_out32) {
+    if (host_out32) VER_CHECK_CUDA(cudaMemcpyFromSymbol(host_out32, g_tc_timing, sizeof(unsigned long long) * 32));
+    unsigned long long zero[32] = {0};
+    VER_CHECK_CUDA(cudaMemcpyToSymbol(g_tc_timing, zero, sizeof(zero)));
+    VER_CHECK_CUDA(cudaMemcpyToSymbol(g_tc_timing_on, &enable, sizeof(int)));
+    return VER_OK;
+}
+
 int ver_tc_supported(int Ncam, int S, int Dh, int NP) {
     if (!(Ncam <= kMaxCam && NP >= 1 && NP <= 8 && S <= 256 && (Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128)))
         return 0;
