@@ -1,0 +1,15 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench, phase timers, ncu launch list + full capture of the sampler kernels.
+# Usage (from the repo root, on the box): bash tools/gpu_round.sh <tag>
+tag=${1:-run}
+out=gpurun_out/$tag
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
+timeout 600 python bench.py --steps 10 --warmup 3 > $out/bench.json 2> $out/bench.err; echo "bench exit $?" >> $out/bench.err
+timeout 300 python tools/tc_timing.py > $out/tc_timing.txt 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sca_.*_tc_kernel -c 2 -o $out/sca_tc \
+    python tools/tc_timing.py > $out/ncu_full.log 2>&1
+tail -3 $out/pytest.log; cat $out/bench.json; tail -2 $out/bench.err; cat $out/tc_timing.txt
