@@ -23,6 +23,7 @@
 #ifndef VER_B200_H_
 #define VER_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -125,6 +126,27 @@ int ver_sca_forward(int dtype, const void* value, int value_layout, const float*
  *   value [Bv, S, NH, Dh] fp16 (VER_LAYOUT_MMCV)  ->  vimg [Bv, NH, Dh/8, SP/8, 8, 8] fp16,
  *   SP = S rounded up to 16, padded pixels zero.  Dh % 8 == 0. */
 int ver_value_image_f16(const void* value, void* vimg, int Bv, int S, int NH, int Dh, ver_stream_t stream);
+
+/* Visibility-sorted voxel order for the tensor-core sampler (ver_sca_forward_sorted).  The device-side
+ * counterpart of the reference's per-camera rebatch (M/spatial_cross_attention.py:138-154: nonzero() per
+ * camera + pad to max_len): per panorama, voxels are stably sorted by their camera bit set, so that 128-row
+ * tiles are seen by (nearly) the same cameras.
+ *   vis_bits   [B, Nq] from ver_point_sampling_f32
+ *   order      [B, Nq] int32 (out): voxel index n of sorted row i
+ *   smask      [B, Nq] uint32 (out): camera bit set of sorted row i
+ *   tile_union [B, ceil(Nq/128)] uint32 (out): OR of the bit sets of rows [128 t, 128 t + 128)
+ *   workspace  device scratch of at least ver_visibility_order_workspace() bytes */
+int ver_visibility_order_workspace(int B, int Nq, size_t* bytes);
+int ver_visibility_order(const uint32_t* vis_bits, int B, int Nq, int32_t* order, uint32_t* smask,
+                         uint32_t* tile_union, void* workspace, size_t workspace_bytes, ver_stream_t stream);
+
+/* ver_sca_forward on visibility-sorted rows (fp16 tcgen05 operand images from ver_value_image_f16):
+ * same result, slots written at their voxel positions.  Requires Ncam <= 32, NP in {4, 8}, S <= 256,
+ * Dh in {32, 64, 96, 128}. */
+int ver_sca_forward_sorted(const void* vimg, const float* logits, int ld_logits, const float* rpc,
+                           const int32_t* order, const uint32_t* smask, const uint32_t* tile_union,
+                           void* slots, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
+                           ver_stream_t stream);
 
 /* Backward of ver_sca_forward.
  *   grad_slots  [B, Nq, NH*Dh] dtype

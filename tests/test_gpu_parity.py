@@ -385,8 +385,30 @@ def _oracle_sample(value, logits, rpc, mask, count, B, Ncam, Nq, NH, Dh, NP=8, S
     return out / count.double().clamp(min=1)[..., None]
 
 
-@pytest.mark.parametrize('Dh,grid,B', [(96, (8, 20, 20), 2), (32, (3, 5, 7), 1), (64, (4, 8, 8), 1)])
-def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B):
+def test_visibility_order_properties():
+    """order.cu: per panorama a stable sort of the voxels by camera bit set (integer work: exact)."""
+    for grid, B, ncam in [((16, 40, 40), 3, 18), ((3, 5, 7), 2, 18), ((4, 15, 15), 1, 6)]:
+        Nq = grid[0] * grid[1] * grid[2]
+        l2i, sh = synth.make_rig(B, ncam, grid, seed=7)
+        _, _, bits, _ = ops.point_sampling(cuda(torch.from_numpy(l2i)), cuda(torch.from_numpy(sh)), PC, *grid)
+        order, smask, tu = (t.cpu() for t in ops.visibility_order(bits))
+        bits = bits.cpu()
+        key = bits.long() & 0xffffffff
+        for b in range(B):
+            ref = torch.sort(key[b], stable=True)
+            assert torch.equal(order[b].long(), ref.indices)
+            assert torch.equal(smask[b].long() & 0xffffffff, ref.values)
+            for t in range(tu.shape[1]):
+                u = 0
+                for m in ref.values[t * 128:(t + 1) * 128].tolist():
+                    u |= m
+                assert (int(tu[b, t]) & 0xffffffff) == u
+
+
+@pytest.mark.parametrize('fwd', ['sorted', 'block'])
+@pytest.mark.parametrize('Dh,grid,B', [(96, (8, 20, 20), 2), (32, (3, 5, 7), 2), (64, (4, 8, 8), 1), (96, (3, 11, 13), 3)])
+def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B, fwd, monkeypatch):
+    monkeypatch.setattr(ops, 'TC_FORWARD', fwd)
     ncam, NH = 18, 8
     Nq = grid[0] * grid[1] * grid[2]
     l2i, sh = synth.make_rig(B, ncam, grid, seed=11)
@@ -450,3 +472,18 @@ def test_full_size_properties():
     s1h = ops.sca_sample(v1.half(), logits, vis, 14, 14, 8, 8)
     s1f = ops.sca_sample(v1.half().float(), logits, vis, 14, 14, 8, 8)
     assert rel_err(s1h, s1f) < 1e-3
+    # the tensor-core samplers (visibility-sorted rows / voxel blocks) agree with the gather at full size,
+    # are linear in `value`, write exact zeros for invisible voxels and are run-to-run deterministic
+    v1h = v1.half().view(B * ncam, 196, 768)
+    for fwd in ('sorted', 'block'):
+        ops.TC_FORWARD = fwd
+        try:
+            t1 = ops.sca_sample_tc(v1h, logits, vis, 14, 14, 8, 8)
+            t1b = ops.sca_sample_tc(v1h, logits, vis, 14, 14, 8, 8)
+            t2 = ops.sca_sample_tc(2 * v1h, logits, vis, 14, 14, 8, 8)
+        finally:
+            ops.TC_FORWARD = 'sorted'
+        assert rel_err(t1, s1f) < 1e-3
+        assert torch.equal(t1, t1b)
+        assert rel_err(t2, 2 * t1.float()) < 1e-3
+        assert (t1[count == 0] == 0).all()

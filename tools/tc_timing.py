@@ -28,6 +28,55 @@ def main():
     value = (torch.randn(B * ncam, 196, NH * Dh, device='cuda', generator=g) * 0.5).half()
     logits = torch.randn(B * Nq, 192, device='cuda', generator=g)
     logits[:, :128] *= 2
+    # ---- sorted-row forward (sca_fwd_tc3_kernel)
+    f3 = _lib.lib.ver_debug_tc3_timing
+    f3.restype = ctypes.c_int
+    f3.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+    names3 = {0: 'W: setup', 1: 'W: item top (logits, softmax)', 4: 'W: tap arithmetic', 2: 'W: wait MMA retire',
+              3: 'W: un-tap', 5: 'W: taps (smem RMW)', 6: 'W: fences + arrive', 7: 'W: epilogue wait MMA',
+              8: 'W: epilogue TMEM->slots', 9: 'C: wait built', 10: 'C: wait V', 11: 'C: MMA issue',
+              12: 'C: V buffer wait + TMA'}
+    ops.TC_FORWARD = 'sorted'
+    order, smask, tu = vis.order
+    ncams = sum(bin(int(x) & 0xffffffff).count('1') for x in tu.flatten().tolist())
+    hits = int(count.sum().item())
+    print(f'sorted tiles: {tu.numel()} tiles, {ncams} (tile, camera) products = {ncams * 128 / hits:.3f} x hits '
+          f'({hits} hits, {hits / (B * Nq):.3f} per voxel)')
+    vimg = ops.value_image(value, NH)
+    slots = torch.empty((B, Nq, NH * Dh), dtype=torch.float16, device='cuda')
+
+    def launch3():
+        _lib.check(_lib.lib.ver_sca_forward_sorted(vimg.data_ptr(), logits.data_ptr(), 192, rpc.data_ptr(),
+                                                   order.data_ptr(), smask.data_ptr(), tu.data_ptr(),
+                                                   slots.data_ptr(), B, ncam, Nq, 14, 14, NH, Dh, 8,
+                                                   torch.cuda.current_stream().cuda_stream))
+    for _ in range(3):
+        launch3()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    ts = []
+    for i in range(10):
+        flush.zero_()
+        ev[0].record()
+        launch3()
+        ev[1].record()
+        torch.cuda.synchronize()
+        ts.append(ev[0].elapsed_time(ev[1]))
+    ts.sort()
+    print(f'sca_fwd_tc3_kernel alone (L2 flushed): median {ts[5] * 1e3:.1f} us, min {ts[0] * 1e3:.1f} us')
+    assert f3(1, None) == 0
+    launch3()
+    torch.cuda.synchronize()
+    out3 = (ctypes.c_ulonglong * 32)()
+    assert f3(0, out3) == 0
+    nct = min(148, B * NH * ((Nq + 255) // 256))
+    print(f'{nct} persistent CTAs, cycles per CTA (thread 0 of group 0 / control thread):')
+    for i in sorted(names3):
+        print(f'  [{i:2d}] {names3[i]:32s} {out3[i] / nct:10.0f}')
+    print(f'  worker total {sum(out3[i] for i in range(9)) / nct:.0f}, control total '
+          f'{sum(out3[i] for i in range(9, 13)) / nct:.0f}')
+    ops.TC_FORWARD = 'block'
     fn = _lib.lib.ver_debug_tc_timing
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]

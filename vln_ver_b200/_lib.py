@@ -44,6 +44,9 @@ def _load():
                                       c_int, c_int, c_int, c_int, c_int, P]),
         'ver_sca_forward': (c_int, [c_int, P, c_int, P, c_int, P, P, P] + [c_int] * 10 + [P]),
         'ver_sca_backward': (c_int, [c_int, P, c_int, P, c_int, P, P, P, P, P, P, P] + [c_int] * 10 + [P]),
+        'ver_visibility_order_workspace': (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),
+        'ver_visibility_order': (c_int, [P, c_int, c_int, P, P, P, P, ctypes.c_size_t, P]),
+        'ver_sca_forward_sorted': (c_int, [P, P, c_int, P, P, P, P, P] + [c_int] * 8 + [P]),
         'ver_value_image_f16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
         'ver_feat_embed': (c_int, [c_int, P, P, P, P, c_int, c_int, c_int, c_int, P]),
         'ver_add_layernorm': (c_int, [c_int, P, P, P, P, P, c_int64, c_int, c_float, P]),

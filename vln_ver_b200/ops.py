@@ -179,12 +179,38 @@ class Visibility:
     def __init__(self, rpc, mask, bits, count, grid):
         self.rpc, self.mask, self.bits, self.count, self.grid = rpc, mask, bits, count, grid
         self._index = None
+        self._order = None
 
     @property
     def index(self):
         if self._index is None:
             self._index = visible_index(self.mask)
         return self._index
+
+    @property
+    def order(self):
+        """(order, smask, tile_union): voxels stably sorted by camera bit set, see visibility_order()."""
+        if self._order is None:
+            self._order = visibility_order(self.bits)
+        return self._order
+
+
+def visibility_order(bits):
+    """Device-side counterpart of the per-camera rebatch (M/spatial_cross_attention.py:138-154) for the
+    tensor-core sampler: bits (B, Nq) int32 -> order (B, Nq) int32, smask (B, Nq) int32,
+    tile_union (B, ceil(Nq/128)) int32."""
+    _need_cuda(bits)
+    bits = _c(bits, torch.int32)
+    B, Nq = bits.shape
+    need = ctypes.c_size_t(0)
+    check(lib.ver_visibility_order_workspace(B, Nq, ctypes.byref(need)))
+    ws = torch.empty((need.value,), dtype=torch.uint8, device=bits.device)
+    order = torch.empty((B, Nq), dtype=torch.int32, device=bits.device)
+    smask = torch.empty((B, Nq), dtype=torch.int32, device=bits.device)
+    tile_union = torch.empty((B, (Nq + 127) // 128), dtype=torch.int32, device=bits.device)
+    check(lib.ver_visibility_order(_ptr(bits), B, Nq, _ptr(order), _ptr(smask), _ptr(tile_union), _ptr(ws),
+                                   need.value, _stream()))
+    return order, smask, tile_union
 
 
 class SCASampleFunction(Function):
@@ -260,6 +286,7 @@ def value_image(value, NH):
 
 
 VER_LAYOUT_TC_IMAGE = 2
+TC_FORWARD = 'sorted'    # 'sorted': sca_fwd_tc3_kernel on visibility-sorted rows; 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
 
 
 class SCASampleTCFunction(Function):
@@ -285,9 +312,15 @@ class SCASampleTCFunction(Function):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.ver_sca_forward(VER_F16, _ptr(vimg), VER_LAYOUT_TC_IMAGE, _ptr(logits), logits.shape[1],
-                                  _ptr(vis.rpc), _ptr(vis.bits), _ptr(slots), B, Ncam, Z, H, W, Sh, Sw,
-                                  NH, Dh, NP, _stream()))
+        if TC_FORWARD == 'sorted' and NP % 4 == 0 and logits.shape[1] % 4 == 0:
+            order, smask, tile_union = vis.order
+            check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
+                                             _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw,
+                                             NH, Dh, NP, _stream()))
+        else:
+            check(lib.ver_sca_forward(VER_F16, _ptr(vimg), VER_LAYOUT_TC_IMAGE, _ptr(logits), logits.shape[1],
+                                      _ptr(vis.rpc), _ptr(vis.bits), _ptr(slots), B, Ncam, Z, H, W, Sh, Sw,
+                                      NH, Dh, NP, _stream()))
         if prof is not None:
             e1.record()
             prof.append((e0, e1))
