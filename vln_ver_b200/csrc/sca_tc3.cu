@@ -32,13 +32,14 @@ constexpr int kF3Workers = 256;
 constexpr int kF3Threads = kF3Workers + 32;
 constexpr int kF3Rows = 128;                 // rows per group = UMMA M
 constexpr int kF3ChunkRows = 2 * kF3Rows;
+constexpr int kF3LgBytes = 96;               // 8 points x (2 offsets + 1 attention logit) fp32 of one (row, head)
 
 struct F3Smem {
-    int a_bytes, v_bytes, off_a[2], off_v[2], off_stage, stage_stride, total;
+    int a_bytes, v_bytes, off_a[2], off_v[2], off_stage, stage_stride, off_lg, total;
     // epilogue staging (per warp: 32 rows x pass_cols fp16, padded rows -> conflict-free 16-byte accesses) turns the
     // row-scattered 16-byte global stores of the accumulator into contiguous runs; Dh = 128 has no room for it
     static __host__ __device__ constexpr bool staged(int Dh) { return Dh <= 96; }
-    static __host__ __device__ constexpr int pass_cols(int Dh) { return Dh % 48 == 0 ? 48 : 32; }
+    static __host__ __device__ constexpr int pass_cols(int) { return 32; }
     __host__ __device__ F3Smem(int Dh, int SP) {
         a_bytes = kF3Rows * SP * 2;
         v_bytes = Dh * SP * 2;
@@ -48,7 +49,8 @@ struct F3Smem {
         off_v[1] = 2 * a_bytes + v_bytes;
         off_stage = off_v[1] + v_bytes;
         stage_stride = pass_cols(Dh) * 2 + 16;
-        total = off_stage + (staged(Dh) ? (kF3Workers / 32) * 32 * stage_stride : 0);
+        off_lg = off_stage + (staged(Dh) ? (kF3Workers / 32) * 32 * stage_stride : 0);
+        total = off_lg + kF3Workers * kF3LgBytes;     // per-worker landing slot of the next item's logits (cp.async)
     }
 };
 
@@ -57,6 +59,23 @@ __device__ __forceinline__ uint32_t koff(int k) { return (uint32_t)(k >> 3) * 12
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
+}
+// loads the compiler may not sink to their first use (register pressure would otherwise expose the DRAM latency)
+__device__ __forceinline__ int ldg_pinned(const int32_t* p) {
+    int v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ldg_pinned(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ uint16_t lds16(uint32_t a) {
     uint16_t v;
@@ -131,7 +150,7 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                    __half* __restrict__ slots, int B, int Ncam, int Nq, int Sh, int Sw, int SP, int NH, int NP,
                    int chunks_per_b, int n_items) {
     const int G = SP >> 3;                       // 8-pixel groups per row
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     const F3Smem L(DH, SP);
     __shared__ __align__(8) uint64_t bar_built[2], bar_mma[2], bar_v[2], bar_vfree[2];
     __shared__ uint32_t s_tmem;
@@ -256,7 +275,6 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         // while item i is processed
         int n_cur = -1, n_nx = -1, n_n2 = -1;
         uint32_t m_cur = 0, u_cur = 0, m_nx = 0, u_nx = 0, m_n2 = 0, u_n2 = 0;
-        float4 raw_nx[6];
         float2 ref_nx = make_float2(0.f, 0.f);
         auto load_ids = [&](int item, int& n_o, uint32_t& m_o, uint32_t& u_o) {
             n_o = -1;
@@ -266,30 +284,81 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             const F3Item q = f3_item(item, NH, chunks_per_b);
             const int tile = 2 * q.chunk + g;
             const int i = tile * kF3Rows + r;
-            if (tile < tiles_per_b) u_o = __ldg(tile_union + (size_t)q.b * tiles_per_b + tile);
+            if (tile < tiles_per_b)
+                u_o = (uint32_t)ldg_pinned(reinterpret_cast<const int32_t*>(tile_union) + (size_t)q.b * tiles_per_b + tile);
             if (i < Nq) {
-                n_o = __ldg(order + (size_t)q.b * Nq + i);
-                m_o = __ldg(smask + (size_t)q.b * Nq + i);
+                n_o = ldg_pinned(order + (size_t)q.b * Nq + i);
+                m_o = (uint32_t)ldg_pinned(reinterpret_cast<const int32_t*>(smask) + (size_t)q.b * Nq + i);
             }
         };
-        auto load_row = [&](int item) {            // uses n_nx / m_nx / u_nx (ids of `item`)
-#pragma unroll
-            for (int i = 0; i < 6; ++i) raw_nx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t lg_slot = smem_u32(smem + L.off_lg) + (uint32_t)tid * kF3LgBytes;
+        auto load_row = [&](int item) {            // uses n_nx / m_nx / u_nx (ids of `item`); logits land in my smem slot
             ref_nx = make_float2(0.f, 0.f);
             if (item >= n_items || n_nx < 0) return;
             const F3Item q = f3_item(item, NH, chunks_per_b);
             const float* row = logits + ((size_t)q.b * Nq + n_nx) * ld;
-            const float4* po = reinterpret_cast<const float4*>(row + q.h * NP * 2);
-            const float4* pl = reinterpret_cast<const float4*>(row + NH * NP * 2 + q.h * NP);
+            const float* po = row + q.h * NP * 2;
+            const float* pl = row + NH * NP * 2 + q.h * NP;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (i * 2 < NP) raw_nx[i] = __ldg(po + i);
-            raw_nx[4] = __ldg(pl);
-            if (NP > 4) raw_nx[5] = __ldg(pl + 1);
+                if (i * 2 < NP) cp_async16(lg_slot + i * 16, po + i * 4);
+            cp_async16(lg_slot + 64, pl);
+            if (NP > 4) cp_async16(lg_slot + 80, pl + 4);
             if (u_nx) {
                 const int c0 = __ffs(u_nx) - 1;
-                if ((m_nx >> c0) & 1u) ref_nx = __ldg(rp2 + ((size_t)c0 * B + q.b) * Nq + n_nx);
+                if ((m_nx >> c0) & 1u) ref_nx = ldg_pinned(rp2 + ((size_t)c0 * B + q.b) * Nq + n_nx);
             }
+        };
+
+        // ---- epilogue of one item: slots[row] = accumulator / max(count, 1), staged through shared memory so that
+        // PPR consecutive lanes write one contiguous run of a row
+        auto epilogue = [&](int n, uint32_t m, uint32_t u, int b, int h) {
+            const float inv_cnt = 1.f / (float)max(__popc(m), 1);
+            const size_t row0 = ((size_t)b * Nq) * NH * DH + (size_t)h * DH;     // + n * NH * DH
+            if constexpr (F3Smem::staged(DH)) {
+                constexpr int PC = F3Smem::pass_cols(DH), PPR = PC / 8;      // channels per pass, 16-B pieces per row
+#pragma unroll
+                for (int c0 = 0; c0 < DH; c0 += PC) {
+                    float vv[PC];
+                    if (u) {                            // warp-uniform (tile property)
+                        tmem_ld_cols<PC>(tm_acc + c0, vv);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < PC; ++i) vv[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < PC; ++i) vv[i] *= inv_cnt;
+                    __syncwarp();                   // previous pass fully read
+                    store_channels16<PC>(reinterpret_cast<__half*>(stage + lane * L.stage_stride), vv);
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < PPR; ++k) {
+                        const int qi = k * 32 + lane, row = qi / PPR, piece = qi % PPR;
+                        const int nr = __shfl_sync(VER_FULL_MASK, n, row);
+                        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * L.stage_stride + piece * 16);
+                        if (nr >= 0)
+                            *reinterpret_cast<uint4*>(slots + row0 + (size_t)nr * NH * DH + c0 + piece * 8) = val;
+                    }
+                }
+            } else {
+                __half* dst = (n >= 0) ? slots + row0 + (size_t)n * NH * DH : nullptr;
+#pragma unroll
+                for (int c0 = 0; c0 < DH; c0 += 32) {
+                    float vv[32];
+                    if (u) {
+                        tmem_ld_cols<32>(tm_acc + c0, vv);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) vv[i] = 0.f;
+                    }
+                    if (dst) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) vv[i] *= inv_cnt;
+                        store_channels16<32>(dst + c0, vv);
+                    }
+                }
+            }
+            tc_fence_before();                       // my tcgen05.ld's precede the next overwrite of the accumulator
         };
 
         F3Timer tw(tid == 0);
@@ -297,6 +366,13 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         load_ids(item, n_nx, m_nx, u_nx);
         load_row(item);
         load_ids(item + gridDim.x, n_n2, m_n2, u_n2);
+        // the epilogue of an item runs inside the first build of the NEXT item (between the MMA wait and the
+        // read-modify-writes), so that the tensor-core round trip of its last batch is covered by the next item's
+        // softmax and tap arithmetic
+        bool pend = false;
+        int pn = -1, pb = 0, ph = 0;
+        uint32_t pm = 0, pu = 0;
+        const int nchunks = SP >> 4;
         tw.lap(0);                                      // setup
         for (; item < n_items; item += gridDim.x) {
             const F3Item q = f3_item(item, NH, chunks_per_b);
@@ -308,6 +384,14 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             // ---- offsets (pixel units) and softmax weights of my row, this head
             float ox[8], oy[8], aw[8];
             {
+                cp_async_wait_all();                    // my slot holds this item's logits (issued one item ago)
+                float4 raw_nx[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(raw_nx[i].x), "=f"(raw_nx[i].y), "=f"(raw_nx[i].z), "=f"(raw_nx[i].w)
+                                 : "r"(lg_slot + i * 16)
+                                 : "memory");
                 float mx = -INFINITY;
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
@@ -330,13 +414,13 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                 for (int p = 0; p < 8; ++p) aw[p] *= inv;
             }
             float2 ref = ref_nx;
-            tw.lap(1);                                  // logits arrive -> softmax / offsets
             // ---- prefetch: logits of the next item (its ids are here), ids of the one after
             n_nx = n_n2;
             m_nx = m_n2;
             u_nx = u_n2;
             load_row(item + gridDim.x);
             load_ids(item + 2 * gridDim.x, n_n2, m_n2, u_n2);
+            tw.lap(1);                                  // item top: softmax / offsets, prefetch issue
 
             // ---- cameras of my tile, ascending (= the reference's accumulation order, :166-168)
             for (uint32_t rest = u; rest; rest &= rest - 1) {
@@ -348,42 +432,65 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                     const uint32_t nr = rest & (rest - 1);
                     if (nr) {
                         const int cn = __ffs(nr) - 1;
-                        if ((m >> cn) & 1u) ref_next = __ldg(rp2 + ((size_t)cn * B + q.b) * Nq + n);
+                        if ((m >> cn) & 1u) ref_next = ldg_pinned(rp2 + ((size_t)cn * B + q.b) * Nq + n);
                     }
                 }
-                // ---- the 32 taps of this (row, camera): offsets, fp16 coefficients, K-chunk mask -- registers only,
-                // overlaps the tensor-core work on my previous batch
+                // ---- the 32 taps of this (row, camera): byte offsets, fp16 coefficients, K-chunk mask -- registers
+                // only, overlaps the tensor-core work on my previous batch.  floor() through the 2^23 trick
+                // (add with round-down): no conversion-pipe instructions
                 uint32_t noff[16], wts[16], kmask = 0;
+                int pixv[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) pixv[p] = -1000 - 64 * p;     // rows / points outside alias nothing
                 if (vis) {
-                    const float rx = ref.x * fSw - 0.5f, ry = ref.y * fSh - 0.5f;
+                    const float rx1 = fmaf(ref.x, fSw, 0.5f), ry1 = fmaf(ref.y, fSh, 0.5f);      // pixel coordinate + 1
 #pragma unroll
                     for (int p = 0; p < 8; ++p) {
-                        const float x = rx + ox[p], y = ry + oy[p];
-                        const bool in = (p < NP) && x > -1.f && y > -1.f && x < fSw && y < fSh;
-                        const float xf = floorf(x), yf = floorf(y);
-                        const float fx = x - xf, fy = y - yf;
-                        const int x0 = (int)xf, y0 = (int)yf;
-                        const bool vx0 = in && x0 >= 0, vx1 = in && x0 + 1 < Sw, vy0 = y0 >= 0, vy1 = y0 + 1 < Sh;
-                        const int pix = y0 * Sw + x0;
+                        const float tx = rx1 + ox[p], ty = ry1 + oy[p];
+                        const float bx = __fadd_rd(tx, 8388608.f), by = __fadd_rd(ty, 8388608.f);
+                        const int ix = __float_as_int(bx) - 0x4B000000, iy = __float_as_int(by) - 0x4B000000;   // x0 + 1, y0 + 1
+                        const bool in = (p < NP) && (unsigned)ix <= (unsigned)Sw && (unsigned)iy <= (unsigned)Sh;
+                        const float fx = tx - (bx - 8388608.f), fy = ty - (by - 8388608.f);
+                        const bool vx0 = in && ix >= 1, vx1 = in && ix < Sw, vy0 = iy >= 1, vy1 = iy < Sh;
+                        const int pix = (iy - 1) * Sw + (ix - 1);
                         const float a = aw[p];
                         const float gx = 1.f - fx, gy = 1.f - fy;
                         const bool v00 = vx0 && vy0, v01 = vx1 && vy0, v10 = vx0 && vy1, v11 = vx1 && vy1;
                         const uint32_t o00 = v00 ? koff(pix) : trash, o01 = v01 ? koff(pix + 1) : trash;
                         const uint32_t o10 = v10 ? koff(pix + Sw) : trash, o11 = v11 ? koff(pix + Sw + 1) : trash;
-                        kmask |= (v00 ? 1u << (pix >> 4) : 0u) | (v01 ? 1u << ((pix + 1) >> 4) : 0u) |
-                                 (v10 ? 1u << ((pix + Sw) >> 4) : 0u) | (v11 ? 1u << ((pix + Sw + 1) >> 4) : 0u);
+                        // chunks of the (up to) two pixel pairs; a neighbour that is out of the map only adds a chunk of zeros
+                        const uint32_t top = (1u << (max(pix, 0) >> 4)) | (1u << ((pix + 1) >> 4));
+                        const uint32_t bot = (1u << ((pix + Sw) >> 4)) | (1u << ((pix + Sw + 1) >> 4));
+                        kmask |= ((in && vy0) ? top : 0u) | ((in && vy1) ? bot : 0u);
                         noff[2 * p] = o00 | (o01 << 16);
                         noff[2 * p + 1] = o10 | (o11 << 16);
                         wts[2 * p] = pack_half2(a * (gy * gx), a * (gy * fx));
                         wts[2 * p + 1] = pack_half2(a * (fy * gx), a * (fy * fx));
+                        if (in) pixv[p] = pix;
                     }
+                    kmask &= (1u << nchunks) - 1u;
+                }
+                // points p and p + 4 are read-modify-written together when their 2x2 cells are disjoint for every row
+                // of the warp (the usual case: their offsets differ by 4 steps), else one after the other
+                bool together[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const uint32_t d = (uint32_t)abs(pixv[p] - pixv[p + 4]);
+                    const bool alias = d <= 1u || (d - (uint32_t)(Sw - 1)) <= 2u;
+                    together[p] = !__any_sync(VER_FULL_MASK, alias);
                 }
                 tw.lap(4);                              // tap arithmetic
                 if (seen < it) {                        // MMAs of my previous batch retired -> A_g is mine again
                     mbar_wait_park(&bar_mma[g], seen & 1);
                     ++seen;
+                    tc_fence_after();
                 }
                 tw.lap(2);                              // wait: my previous MMA batch retired
+                if (pend) {                             // ... which completed the previous item's accumulator
+                    epilogue(pn, pm, pu, pb, ph);
+                    pend = false;
+                }
+                tw.lap(8);                              // epilogue: TMEM -> slots
                 if (tapped) {                           // un-tap: my row is all zero again
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -395,20 +502,40 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                 tw.lap(3);                              // un-tap
                 if (vis) {
                     tapped = true;
+                    // the LSU keeps program order, so consecutive rounds may touch the same element
 #pragma unroll
-                    for (int p = 0; p < 8; ++p) {
-                        // the four corners of a point are four different elements (or the trash column): loads first,
-                        // then stores; points may share elements, so they go in order (the LSU keeps program order)
+                    for (int p = 0; p < 4; ++p) {
+                        const int q2 = p + 4;
                         const uint32_t a0 = myrow + (noff[2 * p] & 0xffffu), a1 = myrow + (noff[2 * p] >> 16);
                         const uint32_t a2 = myrow + (noff[2 * p + 1] & 0xffffu), a3 = myrow + (noff[2 * p + 1] >> 16);
-                        const uint16_t h0 = lds16(a0), h1 = lds16(a1), h2 = lds16(a2), h3 = lds16(a3);
-                        sts16(a0, hadd16(h0, (uint16_t)(wts[2 * p] & 0xffffu)));
-                        sts16(a1, hadd16(h1, (uint16_t)(wts[2 * p] >> 16)));
-                        sts16(a2, hadd16(h2, (uint16_t)(wts[2 * p + 1] & 0xffffu)));
-                        sts16(a3, hadd16(h3, (uint16_t)(wts[2 * p + 1] >> 16)));
-                        off[2 * p] = noff[2 * p];
-                        off[2 * p + 1] = noff[2 * p + 1];
+                        const uint32_t b0 = myrow + (noff[2 * q2] & 0xffffu), b1 = myrow + (noff[2 * q2] >> 16);
+                        const uint32_t b2 = myrow + (noff[2 * q2 + 1] & 0xffffu), b3 = myrow + (noff[2 * q2 + 1] >> 16);
+                        if (together[p]) {
+                            const uint16_t h0 = lds16(a0), h1 = lds16(a1), h2 = lds16(a2), h3 = lds16(a3);
+                            const uint16_t g0 = lds16(b0), g1 = lds16(b1), g2 = lds16(b2), g3 = lds16(b3);
+                            sts16(a0, hadd16(h0, (uint16_t)(wts[2 * p] & 0xffffu)));
+                            sts16(a1, hadd16(h1, (uint16_t)(wts[2 * p] >> 16)));
+                            sts16(a2, hadd16(h2, (uint16_t)(wts[2 * p + 1] & 0xffffu)));
+                            sts16(a3, hadd16(h3, (uint16_t)(wts[2 * p + 1] >> 16)));
+                            sts16(b0, hadd16(g0, (uint16_t)(wts[2 * q2] & 0xffffu)));
+                            sts16(b1, hadd16(g1, (uint16_t)(wts[2 * q2] >> 16)));
+                            sts16(b2, hadd16(g2, (uint16_t)(wts[2 * q2 + 1] & 0xffffu)));
+                            sts16(b3, hadd16(g3, (uint16_t)(wts[2 * q2 + 1] >> 16)));
+                        } else {
+                            const uint16_t h0 = lds16(a0), h1 = lds16(a1), h2 = lds16(a2), h3 = lds16(a3);
+                            sts16(a0, hadd16(h0, (uint16_t)(wts[2 * p] & 0xffffu)));
+                            sts16(a1, hadd16(h1, (uint16_t)(wts[2 * p] >> 16)));
+                            sts16(a2, hadd16(h2, (uint16_t)(wts[2 * p + 1] & 0xffffu)));
+                            sts16(a3, hadd16(h3, (uint16_t)(wts[2 * p + 1] >> 16)));
+                            const uint16_t g0 = lds16(b0), g1 = lds16(b1), g2 = lds16(b2), g3 = lds16(b3);
+                            sts16(b0, hadd16(g0, (uint16_t)(wts[2 * q2] & 0xffffu)));
+                            sts16(b1, hadd16(g1, (uint16_t)(wts[2 * q2] >> 16)));
+                            sts16(b2, hadd16(g2, (uint16_t)(wts[2 * q2 + 1] & 0xffffu)));
+                            sts16(b3, hadd16(g3, (uint16_t)(wts[2 * q2 + 1] >> 16)));
+                        }
                     }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) off[i] = noff[i];
                 }
                 tw.lap(5);                              // taps (shared-memory read-modify-writes)
                 kmask = __reduce_or_sync(VER_FULL_MASK, kmask);
@@ -423,63 +550,34 @@ sca_fwd_tc3_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                 ref = ref_next;
                 tw.lap(6);                              // fences + arrive
             }
-            // ---- epilogue: slots = accumulator / max(count, 1)
+            if (u) {                                    // my last batch is in flight: epilogue deferred
+                pend = true;
+                pn = n;
+                pm = m;
+                pu = u;
+                pb = q.b;
+                ph = q.h;
+            } else {                                    // no camera sees this tile: zeros (after any pending epilogue)
+                if (pend) {
+                    if (seen < it) {
+                        mbar_wait_park(&bar_mma[g], seen & 1);
+                        ++seen;
+                        tc_fence_after();
+                    }
+                    epilogue(pn, pm, pu, pb, ph);
+                    pend = false;
+                }
+                epilogue(n, m, 0u, q.b, q.h);
+            }
+            tw.lap(7);                                  // item end
+        }
+        if (pend) {
             if (seen < it) {
                 mbar_wait_park(&bar_mma[g], seen & 1);
                 ++seen;
+                tc_fence_after();
             }
-            tc_fence_after();
-            tw.lap(7);                                  // epilogue: wait for the last MMAs
-            {
-                const float inv_cnt = 1.f / (float)max(__popc(m), 1);
-                const size_t row0 = ((size_t)q.b * Nq) * NH * DH + (size_t)q.h * DH;     // + n * NH * DH
-                if constexpr (F3Smem::staged(DH)) {
-                    constexpr int PC = F3Smem::pass_cols(DH), PPR = PC / 8;      // channels per pass, 16-B pieces per row
-#pragma unroll
-                    for (int c0 = 0; c0 < DH; c0 += PC) {
-                        float vv[PC];
-                        if (u) {                        // warp-uniform (tile property)
-                            tmem_ld_cols<PC>(tm_acc + c0, vv);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < PC; ++i) vv[i] = 0.f;
-                        }
-#pragma unroll
-                        for (int i = 0; i < PC; ++i) vv[i] *= inv_cnt;
-                        __syncwarp();                   // previous pass fully read
-                        store_channels16<PC>(reinterpret_cast<__half*>(stage + lane * L.stage_stride), vv);
-                        __syncwarp();
-                        // 16-byte pieces, consecutive lanes walk along a row: PPR lanes write one contiguous PC * 2 B run
-#pragma unroll
-                        for (int k = 0; k < PPR; ++k) {
-                            const int qi = k * 32 + lane, row = qi / PPR, piece = qi % PPR;
-                            const int nr = __shfl_sync(VER_FULL_MASK, n, row);
-                            const uint4 val = *reinterpret_cast<const uint4*>(stage + row * L.stage_stride + piece * 16);
-                            if (nr >= 0)
-                                *reinterpret_cast<uint4*>(slots + row0 + (size_t)nr * NH * DH + c0 + piece * 8) = val;
-                        }
-                    }
-                } else {
-                    __half* dst = (n >= 0) ? slots + row0 + (size_t)n * NH * DH : nullptr;
-#pragma unroll
-                    for (int c0 = 0; c0 < DH; c0 += 32) {
-                        float vv[32];
-                        if (u) {
-                            tmem_ld_cols<32>(tm_acc + c0, vv);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) vv[i] = 0.f;
-                        }
-                        if (dst) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) vv[i] *= inv_cnt;
-                            store_channels16<32>(dst + c0, vv);
-                        }
-                    }
-                }
-            }
-            tc_fence_before();                           // my tcgen05.ld's precede the next overwrite of the accumulator
-            tw.lap(8);                                  // epilogue: TMEM -> slots
+            epilogue(pn, pm, pu, pb, ph);
         }
     }
     tc_fence_before();
@@ -492,7 +590,7 @@ int launch_fwd_tc3(const __half* vimg, const float* logits, int ld, const float*
                    const uint32_t* smask, const uint32_t* tile_union, __half* slots, int B, int Ncam, int Nq,
                    int Sh, int Sw, int SP, int NH, int NP, cudaStream_t st) {
     const F3Smem L(DH, SP);
-    VER_CHECK_ARG(L.total + 2048 <= ver_device_max_smem_optin(), "TC forward needs %d B of shared memory", L.total);
+    VER_CHECK_ARG(L.total + 512 <= ver_device_max_smem_optin(), "TC forward needs %d B of shared memory", L.total);
     auto kern = sca_fwd_tc3_kernel<DH>;
     VER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     const int chunks_per_b = (Nq + kF3ChunkRows - 1) / kF3ChunkRows;
@@ -521,7 +619,7 @@ int ver_tc3_supported(int Ncam, int S, int Dh, int NP) {
     if (!(Ncam <= 32 && NP >= 1 && NP <= 8 && S <= 256 && S % 16 != 0 && (Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128)))
         return 0;
     const int SP = (S + 15) / 16 * 16;
-    return F3Smem(Dh, SP).total + 2048 <= ver_device_max_smem_optin();
+    return F3Smem(Dh, SP).total + 512 <= ver_device_max_smem_optin();
 }
 
 /* Forward of the fused SCA sampler on visibility-sorted rows (see include/ver_b200.h). */
