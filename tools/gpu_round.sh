@@ -10,6 +10,8 @@ timeout 600 python bench.py --steps 10 --warmup 3 > $out/bench.json 2> $out/benc
 timeout 300 python tools/tc_timing.py > $out/tc_timing.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:sca_.*_tc_kernel -c 2 -o $out/sca_tc \
-    python tools/tc_timing.py > $out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sca_fwd_tc3_kernel -s 3 -c 1 -o $out/sca_fwd_tc3 \
+    python tools/tc_timing.py > $out/ncu_full_fwd.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sca_bwd_tc_kernel -c 1 -o $out/sca_bwd_tc \
+    python tools/tc_timing.py > $out/ncu_full_bwd.log 2>&1
 tail -3 $out/pytest.log; cat $out/bench.json; tail -2 $out/bench.err; cat $out/tc_timing.txt
