@@ -28,15 +28,20 @@ def main():
     value = (torch.randn(B * ncam, 196, NH * Dh, device='cuda', generator=g) * 0.5).half()
     logits = torch.randn(B * Nq, 192, device='cuda', generator=g)
     logits[:, :128] *= 2
-    # ---- sorted-row forward (sca_fwd_tc3_kernel)
-    f3 = _lib.lib.ver_debug_tc3_timing
-    f3.restype = ctypes.c_int
-    f3.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+    # ---- sorted-row forward: sca_fwd_tc4_kernel (A operand in TMEM) and sca_fwd_tc3_kernel (A image in smem)
+    def hook(name):
+        f = getattr(_lib.lib, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+        return f
     names3 = {0: 'W: setup', 1: 'W: item top (logits, softmax)', 4: 'W: tap arithmetic', 2: 'W: wait MMA retire',
               3: 'W: un-tap', 5: 'W: taps (smem RMW)', 6: 'W: fences + arrive', 7: 'W: epilogue wait MMA',
               8: 'W: epilogue TMEM->slots', 9: 'C: wait built', 10: 'C: wait V', 11: 'C: MMA issue',
               12: 'C: V buffer wait + TMA'}
-    ops.TC_FORWARD = 'sorted'
+    names4 = {0: 'W: setup', 1: 'W: item top (slot, prefetch, softmax)', 4: 'W: taps (arithmetic + RMW)',
+              2: 'W: wait MMA retire', 5: 'W: copy scratch->TMEM + zero', 6: 'W: fences + arrive', 7: 'W: item end',
+              9: 'C: wait built', 10: 'C: wait V', 13: 'C: wait drained accumulator', 11: 'C: MMA issue',
+              12: 'C: V buffer wait + TMA', 16: 'E: wait full accumulator', 17: 'E: TMEM->slots'}
     order, smask, tu = vis.order
     ncams = sum(bin(int(x) & 0xffffffff).count('1') for x in tu.flatten().tolist())
     hits = int(count.sum().item())
@@ -50,32 +55,45 @@ def main():
                                                    order.data_ptr(), smask.data_ptr(), tu.data_ptr(),
                                                    slots.data_ptr(), B, ncam, Nq, 14, 14, NH, Dh, 8,
                                                    torch.cuda.current_stream().cuda_stream))
-    for _ in range(3):
-        launch3()
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(11)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-    ts = []
-    for i in range(10):
-        flush.zero_()
-        ev[0].record()
-        launch3()
-        ev[1].record()
+    ref_out = None
+    for variant, kname, tname, names in ((0, 'sca_fwd_tc4_kernel', 'ver_debug_tc4_timing', names4),
+                                         (3, 'sca_fwd_tc3_kernel', 'ver_debug_tc3_timing', names3)):
+        _lib.lib.ver_debug_sorted_variant(variant)
+        f3 = hook(tname)
+        for _ in range(3):
+            launch3()
         torch.cuda.synchronize()
-        ts.append(ev[0].elapsed_time(ev[1]))
-    ts.sort()
-    print(f'sca_fwd_tc3_kernel alone (L2 flushed): median {ts[5] * 1e3:.1f} us, min {ts[0] * 1e3:.1f} us')
-    assert f3(1, None) == 0
-    launch3()
-    torch.cuda.synchronize()
-    out3 = (ctypes.c_ulonglong * 32)()
-    assert f3(0, out3) == 0
-    nct = min(148, B * NH * ((Nq + 255) // 256))
-    print(f'{nct} persistent CTAs, cycles per CTA (thread 0 of group 0 / control thread):')
-    for i in sorted(names3):
-        print(f'  [{i:2d}] {names3[i]:32s} {out3[i] / nct:10.0f}')
-    print(f'  worker total {sum(out3[i] for i in range(9)) / nct:.0f}, control total '
-          f'{sum(out3[i] for i in range(9, 13)) / nct:.0f}')
+        if ref_out is None:
+            ref_out = slots.clone()
+        else:
+            d = (slots.float() - ref_out.float()).abs().max().item() / ref_out.float().abs().max().item()
+            print(f'  max |tc3 - tc4| / max |tc4| = {d:.2e}')
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ts = []
+        for i in range(10):
+            flush.zero_()
+            ev[0].record()
+            launch3()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]))
+        ts.sort()
+        print(f'{kname} alone (L2 flushed): median {ts[5] * 1e3:.1f} us, min {ts[0] * 1e3:.1f} us')
+        assert f3(1, None) == 0
+        launch3()
+        torch.cuda.synchronize()
+        out3 = (ctypes.c_ulonglong * 32)()
+        assert f3(0, out3) == 0
+        nct = min(148, B * NH * ((Nq + 255) // 256))
+        print(f'{nct} persistent CTAs, cycles per CTA (thread 0 of group 0 / control thread / epilogue warp 8):')
+        for i in sorted(names):
+            print(f'  [{i:2d}] {names[i]:40s} {out3[i] / nct:10.0f}')
+        print(f'  worker total {sum(out3[i] for i in range(9)) / nct:.0f}, control total '
+              f'{sum(out3[i] for i in range(9, 14)) / nct:.0f}')
+    _lib.lib.ver_debug_sorted_variant(0)
+    if '--fwd-only' in sys.argv:
+        return
     ops.TC_FORWARD = 'block'
     fn = _lib.lib.ver_debug_tc_timing
     fn.restype = ctypes.c_int

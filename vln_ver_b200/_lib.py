@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libver_b200.so')
 
 VER_F32, VER_F16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class VerError(RuntimeError):
@@ -53,10 +53,12 @@ def _load():
         'ver_dropout_add_layernorm_fwd': (c_int, [c_int, P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float,
                                                   ctypes.c_uint64, P]),
         'ver_dropout_add_layernorm_bwd_blocks': (c_int, [c_int64]),
-        'ver_dropout_add_layernorm_bwd': (c_int, [c_int, P, P, P, P, P, P, P, P, c_int64, c_int, c_float,
+        'ver_dropout_add_layernorm_bwd': (c_int, [c_int, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_float,
                                                   ctypes.c_uint64, P]),
         'ver_relu_dropout_fwd': (c_int, [c_int, P, P, c_int64, c_float, ctypes.c_uint64, P]),
-        'ver_relu_dropout_bwd': (c_int, [c_int, P, P, P, c_int64, c_float, P]),
+        'ver_colsum_partial_rows': (c_int, []),
+        'ver_relu_dropout_bwd': (c_int, [c_int, P, P, P, c_int64, c_float, c_int, P, P]),
+        'ver_cast_colsum': (c_int, [c_int, P, P, c_int64, c_int, P, P]),
         'ver_focal_loss': (c_int, [P, P, c_int, P, P, P, P, c_int64, c_int, c_float, c_float, P]),
         'ver_occupancy_decode': (c_int, [P, c_int64, c_int, c_float, P, P, P, P]),
     }
@@ -64,6 +66,8 @@ def _load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    lib.ver_debug_sorted_variant.restype = c_int        # debug hook (not part of the declared ABI)
+    lib.ver_debug_sorted_variant.argtypes = [c_int]
     if lib.ver_abi_version() != ABI_VERSION:
         raise VerError(f'libver_b200.so ABI {lib.ver_abi_version()} != expected {ABI_VERSION}')
     return lib, tuple(sig)

@@ -11,10 +11,10 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 LIB = os.path.join(HERE, 'libver_b200.so')
 STAMP = os.path.join(HERE, '.libver_b200.stamp')
 
-SOURCES = ['api.cu', 'geometry.cu', 'msda.cu', 'sca.cu', 'sca_tc.cu', 'sca_tc3.cu', 'order.cu', 'elementwise.cu',
+SOURCES = ['api.cu', 'geometry.cu', 'msda.cu', 'sca.cu', 'sca_tc.cu', 'sca_tc3.cu', 'sca_tc4.cu', 'order.cu', 'elementwise.cu',
            'fused_norm.cu']
 NVCC_FLAGS = ['--threads', '8', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '--shared', '-I', INCLUDE]
+              '-Xcompiler', '-fPIC', '--shared']
 
 
 def _digest():
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
             if f.read().strip() == digest:
                 return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc_path()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + srcs
+    cmd = [nvcc_path()] + NVCC_FLAGS + ['-I', INCLUDE] + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + srcs
     if verbose:
         print(' '.join(cmd))
     subprocess.run(cmd, check=True)

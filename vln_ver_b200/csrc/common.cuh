@@ -42,6 +42,11 @@ int ver_sca_backward_tc(const void* vimg, const float* logits, int ld, const flo
                         const int32_t* counts, const int32_t* index, const void* gslots, float* gvalue,
                         float* glogits, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
                         cudaStream_t st);
+// TMEM-operand sorted-row forward, sca_tc4.cu
+int ver_tc4_supported(int Ncam, int S, int Dh, int NP);
+int ver_sca_forward_tc4(const void* vimg, const float* logits, int ld, const float* rpc, const int32_t* order,
+                        const uint32_t* smask, const uint32_t* tile_union, void* slots, int B, int Ncam, int Nq,
+                        int Sh, int Sw, int NH, int Dh, int NP, cudaStream_t st);
 int ver_device_sm_count();
 int ver_device_max_smem_optin();
 

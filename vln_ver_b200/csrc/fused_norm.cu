@@ -169,45 +169,58 @@ dropout_add_ln_fwd(const T* __restrict__ x, const T* __restrict__ res, const flo
 
 // ---------------------------------------------------------------- backward
 // dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
-// d residual = dz ; dx = dz * keep / (1-p) ; partial dgamma/dbeta per block
+// d residual = dz ; dx = dz * keep / (1-p) ; per-block partial column sums of dgamma, dbeta and (optionally) dx --
+// the latter is the bias gradient of the Linear that produced x (output_proj / the FFN's last Linear).
+// Register budget: the packed dy / z vectors are kept between the statistics pass and the dz pass and unpacked
+// twice, so that the three accumulator sets (9 x NV x 8 floats) fit in 128 registers -> 2 CTAs (16 warps) per SM.
 template <typename T, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const float2* __restrict__ stats,
                    const float* __restrict__ gamma, T* __restrict__ dx, T* __restrict__ dres,
-                   float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int64_t rows, int C,
-                   float p, uint64_t seed) {
-    extern __shared__ float s_part[];       // [2][8 warps][C]
+                   float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, float* __restrict__ dxsum_part,
+                   int64_t rows, int C, float p, uint64_t seed) {
+    extern __shared__ float s_part[];       // [8 warps][C], reused for the three reductions
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t thr16 = (uint32_t)(p * 65536.f);
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-    float dg[NV][8], db[NV][8];
+    float dg[NV][8], db[NV][8], ds[NV][8];
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = 0.f;
+        for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = ds[k][e] = 0.f;
+    auto load_gamma = [&](int c, float (&gm)[8]) {           // L1-resident after the first row
+        const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + c)),
+                     b = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+        gm[0] = a.x; gm[1] = a.y; gm[2] = a.z; gm[3] = a.w; gm[4] = b.x; gm[5] = b.y; gm[6] = b.z; gm[7] = b.w;
+    };
 
     for (int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + warp; row < rows;
          row += (int64_t)gridDim.x * kRowsPerBlock) {
         const float2 st = stats[row];
-        float g[NV][8], xh[NV][8];
+        Vec8<T> vy[NV], vz[NV];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int c = (k * 32 + lane) * 8;
             if (c < C) {
-                Vec8<T> a, b;
-                float fy[8], fz[8];
-                a.load(dy + row * C + c);
-                a.get(fy);
-                b.load(z + row * C + c);
-                b.get(fz);
+                vy[k].load(dy + row * C + c);
+                vz[k].load(z + row * C + c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+                float fy[8], fz[8], gm[8];
+                vy[k].get(fy);
+                vz[k].get(fz);
+                load_gamma(c, gm);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    xh[k][e] = (fz[e] - st.x) * st.y;
-                    g[k][e] = fy[e] * gamma[c + e];
-                    s1 += g[k][e];
-                    s2 += g[k][e] * xh[k][e];
-                    dg[k][e] += fy[e] * xh[k][e];
+                    const float xh = (fz[e] - st.x) * st.y, g = fy[e] * gm[e];
+                    s1 += g;
+                    s2 += g * xh;
+                    dg[k][e] += fy[e] * xh;
                     db[k][e] += fy[e];
                 }
             }
@@ -222,9 +235,15 @@ dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const floa
         for (int k = 0; k < NV; ++k) {
             const int c = (k * 32 + lane) * 8;
             if (c < C) {
-                float dz[8];
+                float fy[8], fz[8], dz[8], gm[8];
+                vy[k].get(fy);
+                vz[k].get(fz);
+                load_gamma(c, gm);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) dz[e] = st.y * (g[k][e] - m1 - xh[k][e] * m2);
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (fz[e] - st.x) * st.y;
+                    dz[e] = st.y * (fy[e] * gm[e] - m1 - xh * m2);
+                }
                 Vec8<T> o;
                 if (dres) {
                     o.set(dz);
@@ -237,34 +256,36 @@ dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const floa
                 }
                 o.set(dz);
                 o.store(dx + row * C + c);
+                if (dxsum_part) {          // what was stored (rounded to T) is what the bias gradient sums
+                    o.get(dz);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ds[k][e] += dz[e];
+                }
             }
         }
     }
-    // block-level reduction of the parameter-gradient partials
-    float* sg = s_part;
-    float* sb = s_part + 8 * C;
+    // block-level reduction of the parameter-gradient partials, one quantity at a time through [8][C] floats
+    auto reduce = [&](float (&acc)[NV][8], float* out) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const int c = (k * 32 + lane) * 8;
-        if (c < C) {
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                sg[warp * C + c + e] = dg[k][e];
-                sb[warp * C + c + e] = db[k][e];
+                for (int e = 0; e < 8; ++e) s_part[warp * C + c + e] = acc[k][e];
             }
         }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = 0.f, b = 0.f;
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            a += sg[w * C + c];
-            b += sb[w * C + c];
+            for (int w = 0; w < 8; ++w) a += s_part[w * C + c];
+            out[(size_t)blockIdx.x * C + c] = a;
         }
-        dgamma_part[(size_t)blockIdx.x * C + c] = a;
-        dbeta_part[(size_t)blockIdx.x * C + c] = b;
-    }
+        __syncthreads();
+    };
+    reduce(dg, dgamma_part);
+    reduce(db, dbeta_part);
+    if (dxsum_part) reduce(ds, dxsum_part);
 }
 
 // ---------------------------------------------------------------- h = dropout(relu(a)), in place capable
@@ -286,10 +307,17 @@ relu_dropout_fwd(const T* __restrict__ a, T* __restrict__ h, int64_t n8, float p
     }
 }
 // da = dh * [h > 0] / (1 - p)   (a kept element with relu(a) == 0 has zero gradient either way)
+// Optional column sums of da (= bias gradient of the FFN's first Linear): the launch makes gridDim * blockDim a
+// multiple of C / 8, so a thread meets the same 8 columns in every iteration and keeps 8 partial sums; thread t of
+// the grid writes them to part[t][8] and the caller sums the rows with equal t % (C / 8).
 template <typename T>
 __global__ void __launch_bounds__(256)
-relu_dropout_bwd(const T* __restrict__ dh, const T* __restrict__ h, T* __restrict__ da, int64_t n8, float p) {
+relu_dropout_bwd(const T* __restrict__ dh, const T* __restrict__ h, T* __restrict__ da, int64_t n8, float p,
+                 float* __restrict__ part) {
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         Vec8<T> vg, vh;
         float g[8], f[8];
@@ -301,8 +329,44 @@ relu_dropout_bwd(const T* __restrict__ dh, const T* __restrict__ h, T* __restric
         for (int e = 0; e < 8; ++e) g[e] = f[e] > 0.f ? g[e] * scale : 0.f;
         vg.set(g);
         vg.store(da + i * 8);
+        if (part) {
+            vg.get(g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += g[e];
+        }
+    }
+    if (part) {
+        float4* o = reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
 }
+
+// y = T(x) for fp32 x, plus the column sums of x (same partial-sum scheme): the fp32 gradients the sampler's backward
+// produces (grad_value, grad_logits) become GEMM operands and bias gradients in one pass
+template <typename T>
+__global__ void __launch_bounds__(256)
+cast_colsum_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n8, float* __restrict__ part) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec8<float> v;
+        float f[8];
+        v.load(x + i * 8);
+        v.get(f);
+        Vec8<T> o;
+        o.set(f);
+        o.store(y + i * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    float4* o = reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+constexpr int kColsumGrid = 148 * 12;      // x 256 threads: a multiple of 3 * 256, i.e. of C / 8 for C | 6144
 
 int ln_grid(int64_t rows) {
     const int64_t need = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
@@ -344,27 +408,28 @@ extern "C" int ver_dropout_add_layernorm_bwd_blocks(int64_t rows) { return ln_gr
 
 extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const void* z, const float* stats,
                                              const float* gamma, void* dx, void* dresidual,
-                                             float* dgamma_part, float* dbeta_part, int64_t rows, int C,
-                                             float p_drop, uint64_t seed, ver_stream_t stream) {
+                                             float* dgamma_part, float* dbeta_part, float* dxsum_part,
+                                             int64_t rows, int C, float p_drop, uint64_t seed,
+                                             ver_stream_t stream) {
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
     VER_CHECK_ARG(dy && z && stats && gamma && dx && dgamma_part && dbeta_part, "null pointer");
     VER_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 1024, "C must be a multiple of 8, <= 1024 (got %d)", C);
     cudaStream_t st = (cudaStream_t)stream;
     const int nv = (C + 255) / 256;
     const int grid = ln_grid(rows);
-    const size_t smem = (size_t)2 * 8 * C * sizeof(float);
+    const size_t smem = (size_t)8 * C * sizeof(float);
     if (dtype == VER_F16) {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        LN_DISPATCH(dropout_add_ln_bwd, __half, nv, <<<grid, 256, smem, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, rows, C, p_drop, seed));
+        LN_DISPATCH(dropout_add_ln_bwd, __half, nv, <<<grid, 256, smem, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed));
     } else {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(dropout_add_ln_bwd<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(dropout_add_ln_bwd<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        LN_DISPATCH(dropout_add_ln_bwd, float, nv, <<<grid, 256, smem, st>>>((const float*)dy, (const float*)z, (const float2*)stats, gamma, (float*)dx, (float*)dresidual, dgamma_part, dbeta_part, rows, C, p_drop, seed));
+        LN_DISPATCH(dropout_add_ln_bwd, float, nv, <<<grid, 256, smem, st>>>((const float*)dy, (const float*)z, (const float2*)stats, gamma, (float*)dx, (float*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed));
     }
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
@@ -385,15 +450,37 @@ extern "C" int ver_relu_dropout_fwd(int dtype, const void* a, void* h, int64_t n
     return VER_OK;
 }
 
+extern "C" int ver_colsum_partial_rows(void) { return kColsumGrid * 256; }
+
 extern "C" int ver_relu_dropout_bwd(int dtype, const void* dh, const void* h, void* da, int64_t n, float p_drop,
-                                    ver_stream_t stream) {
+                                    int C, float* colsum_part, ver_stream_t stream) {
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
     VER_CHECK_ARG(dh && h && da && n > 0 && n % 8 == 0, "bad arguments (n %% 8 != 0?)");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n8 = n / 8;
-    const int grid = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
-    if (dtype == VER_F16) relu_dropout_bwd<__half><<<grid, 256, 0, st>>>((const __half*)dh, (const __half*)h, (__half*)da, n8, p_drop);
-    else relu_dropout_bwd<float><<<grid, 256, 0, st>>>((const float*)dh, (const float*)h, (float*)da, n8, p_drop);
+    int grid = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+    if (colsum_part) {
+        VER_CHECK_ARG(C > 0 && C % 8 == 0 && ((int64_t)kColsumGrid * 256) % (C / 8) == 0 && n % C == 0,
+                      "column sums need C / 8 to divide %d (got C = %d)", kColsumGrid * 256, C);
+        grid = kColsumGrid;
+    }
+    if (dtype == VER_F16) relu_dropout_bwd<__half><<<grid, 256, 0, st>>>((const __half*)dh, (const __half*)h, (__half*)da, n8, p_drop, colsum_part);
+    else relu_dropout_bwd<float><<<grid, 256, 0, st>>>((const float*)dh, (const float*)h, (float*)da, n8, p_drop, colsum_part);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+extern "C" int ver_cast_colsum(int dtype, const float* x, void* y, int64_t rows, int C, float* colsum_part,
+                               ver_stream_t stream) {
+    VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
+    VER_CHECK_ARG(x && y && colsum_part && rows > 0, "bad arguments");
+    VER_CHECK_ARG(C > 0 && C % 8 == 0 && ((int64_t)kColsumGrid * 256) % (C / 8) == 0,
+                  "column sums need C / 8 to divide %d (got C = %d)", kColsumGrid * 256, C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n8 = rows * C / 8;
+    if (dtype == VER_F16) cast_colsum_kernel<__half><<<kColsumGrid, 256, 0, st>>>(x, (__half*)y, n8, colsum_part);
+    else cast_colsum_kernel<float><<<kColsumGrid, 256, 0, st>>>(x, (float*)y, n8, colsum_part);
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;

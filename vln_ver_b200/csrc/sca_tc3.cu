@@ -614,6 +614,13 @@ extern "C" int ver_debug_tc3_timing(int enable, unsigned long long* host_out32) 
     return VER_OK;
 }
 
+// debug: 0 = newest kernel that covers the shape (default), 3 = force sca_fwd_tc3_kernel (A/B timing in tools/)
+static int g_sorted_variant = 0;
+extern "C" int ver_debug_sorted_variant(int v) {
+    g_sorted_variant = v;
+    return VER_OK;
+}
+
 int ver_tc3_supported(int Ncam, int S, int Dh, int NP) {
     // S % 16 != 0: the padded pixel columns of the operand images double as the sink of out-of-map corners
     if (!(Ncam <= 32 && NP >= 1 && NP <= 8 && S <= 256 && S % 16 != 0 && (Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128)))
@@ -637,6 +644,9 @@ extern "C" int ver_sca_forward_sorted(const void* vimg, const float* logits, int
     }
     const int SP = (Sh * Sw + 15) / 16 * 16;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_sorted_variant != 3 && Sh >= 2 && Sw >= 2 && ver_tc4_supported(Ncam, Sh * Sw, Dh, NP))
+        return ver_sca_forward_tc4(vimg, logits, ld_logits, rpc, order, smask, tile_union, slots, B, Ncam, Nq, Sh, Sw,
+                                   NH, Dh, NP, st);
 #define FWD3(D)                                                                                                   \
     launch_fwd_tc3<D>((const __half*)vimg, logits, ld_logits, rpc, order, smask, tile_union, (__half*)slots, B, \
                       Ncam, Nq, Sh, Sw, SP, NH, NP, st)

@@ -1,0 +1,230 @@
+"""One VoxelFormerLayer ('cross_attn', 'norm', 'ffn', 'norm'; vocc.py:136-137) as ONE autograd node with a
+hand-written backward, for fp16 storage on CUDA.
+
+Same arithmetic as the module-by-module path (M/voxel_encoder.py:344-464 -> M/spatial_cross_attention.py:76-176,
+mmcv FFN, LayerNorm); what changes is the plumbing around the sm_100a kernels and the library GEMMs:
+  * fp16 copies of the fp32 master weights are made once per optimizer step (cache keyed on the parameter
+    version), not once per Linear call;
+  * the offset / attention-weight logits come out of ONE fp16 x fp16 -> fp32 GEMM with the fp32 bias as the
+    beta term (no fp16 round trip, no separate cast and bias passes over the (B Nq, 192) tensor);
+  * bias gradients are column sums produced by the kernels that already stream the gradient
+    (ver_dropout_add_layernorm_bwd's dx sums, ver_relu_dropout_bwd, ver_cast_colsum) instead of separate
+    reduction passes; weight gradients are fp16 x fp16 -> fp32 GEMMs written straight in the master precision;
+  * residual-branch gradients are accumulated by the GEMM that produces the other branch (beta = 1) instead
+    of a separate add.
+torch is used for memory, streams and the plain library GEMMs; there is no CPU path.
+"""
+import torch
+from torch.autograd.function import Function, once_differentiable
+
+from . import ops
+from ._lib import VER_F16, check, lib
+from .ops import _ptr, _stream
+
+_HALF_CACHE = {}
+
+
+def half_of(*params):
+    """fp16 copy of a parameter (or the row-concatenation of several), refreshed when a parameter changes."""
+    key = tuple(id(p) for p in params)
+    ver = tuple((p._version, p.data_ptr()) for p in params)
+    hit = _HALF_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        t = params[0].detach().to(torch.float16) if len(params) == 1 else \
+            torch.cat([p.detach() for p in params], 0).to(torch.float16)
+    _HALF_CACHE[key] = (ver, t)
+    return t
+
+
+def f32_cat(*params):
+    key = ('f32',) + tuple(id(p) for p in params)
+    ver = tuple((p._version, p.data_ptr()) for p in params)
+    hit = _HALF_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        t = torch.cat([p.detach().float() for p in params], 0).contiguous()
+    _HALF_CACHE[key] = (ver, t)
+    return t
+
+
+# ------------------------------------------------------------------ thin kernel wrappers (no autograd)
+def _ln_fwd(x, res, gamma32, beta32, p, eps, seed, save):
+    rows, C = x.shape
+    y = torch.empty_like(x)
+    z = torch.empty_like(x) if save else None
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if save else None
+    check(lib.ver_dropout_add_layernorm_fwd(VER_F16, _ptr(x), _ptr(res), _ptr(gamma32), _ptr(beta32), _ptr(y),
+                                            _ptr(z), _ptr(stats), rows, C, float(eps), float(p), seed, _stream()))
+    return y, z, stats
+
+
+def _ln_bwd(dy, z, stats, gamma32, p, seed):
+    """-> dx (gradient of the dropout input), dres (gradient of the residual input), dgamma, dbeta, colsum(dx)."""
+    rows, C = z.shape
+    dx, dres = torch.empty_like(z), torch.empty_like(z)
+    nb = lib.ver_dropout_add_layernorm_bwd_blocks(rows)
+    part = torch.empty((3, nb, C), dtype=torch.float32, device=z.device)
+    check(lib.ver_dropout_add_layernorm_bwd(VER_F16, _ptr(dy), _ptr(z), _ptr(stats), _ptr(gamma32), _ptr(dx),
+                                            _ptr(dres), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), rows, C,
+                                            float(p), seed, _stream()))
+    sums = part.sum(1)
+    return dx, dres, sums[0], sums[1], sums[2]
+
+
+def _colsum_part(device):
+    return torch.empty((lib.ver_colsum_partial_rows(), 8), dtype=torch.float32, device=device)
+
+
+def _fold(part, C):
+    return part.view(-1, C // 8, 8).sum(0).view(C)
+
+
+def _relu_dropout_bwd_(dh, h, p):
+    """in place on dh -> da; returns colsum(da)."""
+    C = h.shape[-1]
+    part = _colsum_part(h.device)
+    check(lib.ver_relu_dropout_bwd(VER_F16, _ptr(dh), _ptr(h), _ptr(dh), h.numel(), float(p), C, _ptr(part),
+                                   _stream()))
+    return _fold(part, C)
+
+
+def _cast_colsum(x32):
+    rows, C = x32.shape
+    y = torch.empty((rows, C), dtype=torch.float16, device=x32.device)
+    part = _colsum_part(x32.device)
+    check(lib.ver_cast_colsum(VER_F16, _ptr(x32), _ptr(y), rows, C, _ptr(part), _stream()))
+    return y, _fold(part, C)
+
+
+def supported(q, feat, vis, NH, NP, S):
+    C = q.shape[-1]
+    return (q.is_cuda and q.dtype == torch.float16 and feat.dtype == torch.float16 and vis is not None
+            and vis.bits is not None and C % 8 == 0 and C <= 1024 and NP % 4 == 0 and (NH * NP * 3) % 4 == 0
+            and ops.tc_supported(torch.float16, vis.rpc.shape[0], S, C // NH, NP)
+            and (lib.ver_colsum_partial_rows() % (C // 8) == 0))
+
+
+class VoxelLayerFunction(Function):
+    """y2 = layer(q): q (B*Nq, C) fp16, feat (Bv*S, C) fp16 (view tokens + camera / level embeddings)."""
+
+    @staticmethod
+    def forward(ctx, q, feat, vis, cfg, Wv, bv, Wso, bso, Waw, baw, Wo, bo, g1, be1, W1, b1, W2, b2, g2, be2):
+        NH, NP, Sh, Sw = cfg['NH'], cfg['NP'], cfg['Sh'], cfg['Sw']
+        training = cfg['training']
+        p_attn = cfg['p_attn'] if training else 0.0
+        p_ffn = cfg['p_ffn'] if training else 0.0
+        p_out = cfg['p_out'] if training else 0.0
+        eps1, eps2 = cfg['eps1'], cfg['eps2']
+        Ncam, B = vis.rpc.shape[:2]
+        Z, H, W = vis.grid
+        Nq, S = Z * H * W, Sh * Sw
+        C = q.shape[1]
+        Dh = C // NH
+        Bv = B * Ncam
+        assert q.shape[0] == B * Nq and feat.shape == (Bv * S, C)
+        q = q.contiguous()
+        feat = feat.contiguous()
+        need_bwd = any(ctx.needs_input_grad)
+
+        Wv16, Wo16, W116, W216 = half_of(Wv), half_of(Wo), half_of(W1), half_of(W2)
+        Wcat16 = half_of(Wso, Waw)
+        bcat32 = f32_cat(bso, baw)
+        # value_proj (M/spatial_cross_attention.py:336) and its tcgen05 operand image
+        v = torch.addmm(half_of(bv), feat, Wv16.t())
+        vimg = ops.value_image(v.view(Bv, S, C), NH)
+        del v
+        # sampling_offsets (+) attention_weights once per voxel (:340-343), fp32 out
+        logits = torch.addmm(bcat32, q, Wcat16.t(), out_dtype=torch.float32)
+        slots = torch.empty((B * Nq, C), dtype=torch.float16, device=q.device)
+        order, smask, tile_union = vis.order
+        prof = ops.PROFILE_EVENTS
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        lib.ver_debug_sorted_variant(3 if ops.TC_FORWARD == 'sorted3' else 0)
+        check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
+                                         _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw, NH, Dh, NP,
+                                         _stream()))
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1))
+        # output_proj, dropout + residual + LayerNorm (:174-176, 'norm')
+        proj = torch.addmm(half_of(bo), slots, Wo16.t())
+        seed1, seed2, seed3 = ops._next_seed(), ops._next_seed(), ops._next_seed()
+        g1f, be1f, g2f, be2f = (t.detach().float().contiguous() for t in (g1, be1, g2, be2))
+        y1, z1, st1 = _ln_fwd(proj, q, g1f, be1f, p_attn, eps1, seed1, need_bwd)
+        del proj
+        # FFN: Linear -> ReLU -> Dropout -> Linear -> Dropout, + identity, LayerNorm
+        h = torch.addmm(half_of(b1), y1, W116.t())
+        check(lib.ver_relu_dropout_fwd(VER_F16, _ptr(h), _ptr(h), h.numel(), float(p_ffn), seed2, _stream()))
+        f = torch.addmm(half_of(b2), h, W216.t())
+        y2, z2, st2 = _ln_fwd(f, y1, g2f, be2f, p_out, eps2, seed3, need_bwd)
+        del f
+        if need_bwd:
+            ctx.save_for_backward(q, feat, vimg, logits, slots, z1, st1, y1, h, z2, st2, Wv16, Wcat16, Wo16, W116,
+                                  W216, g1f, g2f)
+            ctx.vis, ctx.dims = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP)
+            ctx.drop = (p_attn, seed1, p_ffn, p_out, seed3)
+            ctx.n_so = Wso.shape[0]
+            ctx.pdtypes = [t.dtype for t in (Wv, bv, Wso, bso, Waw, baw, Wo, bo, g1, be1, W1, b1, W2, b2, g2, be2)]
+        return y2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy2):
+        (q, feat, vimg, logits, slots, z1, st1, y1, h, z2, st2, Wv16, Wcat16, Wo16, W116, W216, g1f,
+         g2f) = ctx.saved_tensors
+        vis = ctx.vis
+        B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP = ctx.dims
+        p_attn, seed1, p_ffn, p_out, seed3 = ctx.drop
+        f32 = torch.float32
+        dy2 = dy2.contiguous()
+        if dy2.dtype != torch.float16:
+            dy2 = dy2.to(torch.float16)
+        # ---- norm 2 / FFN
+        df, dy1, dg2, dbe2, db2 = _ln_bwd(dy2, z2, st2, g2f, p_out, seed3)
+        dW2 = torch.mm(df.t(), h, out_dtype=f32)
+        dh = torch.mm(df, W216)
+        del df
+        db1 = _relu_dropout_bwd_(dh, h, p_ffn)              # dh -> da in place
+        dW1 = torch.mm(dh.t(), y1, out_dtype=f32)
+        dy1.addmm_(dh, W116)                                # + residual branch, accumulated by the GEMM
+        del dh
+        # ---- norm 1 / output_proj
+        dproj, dq, dg1, dbe1, dbo = _ln_bwd(dy1, z1, st1, g1f, p_attn, seed1)
+        del dy1
+        dWo = torch.mm(dproj.t(), slots, out_dtype=f32)
+        dslots = torch.mm(dproj, Wo16)
+        del dproj
+        # ---- fused sampler backward (A5 backward + SCA scatter)
+        counts, index = vis.index
+        Bv, S, C = B * Ncam, Sh * Sw, NH * Dh
+        gvalue = torch.empty((Bv * S, C), dtype=f32, device=q.device)
+        glogits = torch.empty(logits.shape, dtype=f32, device=q.device)
+        check(lib.ver_sca_backward(VER_F16, _ptr(vimg), ops.VER_LAYOUT_TC_IMAGE, _ptr(logits), logits.shape[1],
+                                   _ptr(vis.rpc), _ptr(vis.bits), _ptr(counts), _ptr(index), _ptr(dslots),
+                                   _ptr(gvalue), _ptr(glogits), B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, _stream()))
+        del dslots
+        # ---- logits Linear (once per voxel): dW, db, and the query gradient joins the residual branch's
+        gl16, dbcat = _cast_colsum(glogits)
+        del glogits
+        dWcat = torch.mm(gl16.t(), q, out_dtype=f32)
+        dq.addmm_(gl16, Wcat16)
+        del gl16
+        # ---- value_proj
+        gv16, dbv = _cast_colsum(gvalue)
+        del gvalue
+        dWv = torch.mm(gv16.t(), feat, out_dtype=f32)
+        dfeat = torch.mm(gv16, Wv16) if ctx.needs_input_grad[1] else None
+        n_so = ctx.n_so
+        grads = [dWv, dbv, dWcat[:n_so], dbcat[:n_so], dWcat[n_so:], dbcat[n_so:], dWo, dbo, dg1, dbe1, dW1, db1,
+                 dW2, db2, dg2, dbe2]
+        grads = [g if g.dtype == dt else g.to(dt) for g, dt in zip(grads, ctx.pdtypes)]
+        return (dq if ctx.needs_input_grad[0] else None, dfeat, None, None, *grads)
+
+
+def voxel_layer(q, feat, vis, cfg, params):
+    return VoxelLayerFunction.apply(q, feat, vis, cfg, *params)

@@ -191,11 +191,50 @@ class VoxelFormerLayer(MyCustomBaseTransformerLayer):
                          norm_cfg=norm_cfg, ffn_num_fcs=ffn_num_fcs, **kwargs)
         self.fp16_enabled = False
         self.fuse_epilogues = True
+        self.fuse_layer = True          # fp16 storage on CUDA: the whole layer as one autograd node (fused_layer.py)
+
+    def _fused_layer_forward(self, query, value, query_pos, kwargs):
+        """The vocc.py layer ('cross_attn', 'norm', 'ffn', 'norm') with fp16 storage as ONE autograd node with a
+        hand-written backward (vln_ver_b200/fused_layer.py); returns None when the configuration is not covered."""
+        from .. import fused_layer
+        if not (self.fuse_layer and not self.pre_norm and query.is_cuda and query_pos is None
+                and tuple(self.operation_order) == ('cross_attn', 'norm', 'ffn', 'norm')):
+            return None
+        attn, ffn = self.attentions[0], self.ffns[0]
+        if not (isinstance(attn, SpatialCrossAttention) and attn.sampler != 'gather'
+                and attn.compute_dtype == torch.float16 and getattr(ffn, 'compute_dtype', None) == torch.float16
+                and getattr(ffn, 'fusable', lambda: False)()):
+            return None
+        vis = kwargs.get('visibility')
+        hw = kwargs.get('spatial_hw')
+        da = attn.deformable_attention
+        if vis is None or hw is None or da.num_levels != 1 or value is None or value.dim() != 4:
+            return None
+        num_cams, l, bs, C = value.shape
+        if query.shape[0] != bs or hw[0] * hw[1] != l:
+            return None
+        q2 = query.to(torch.float16).reshape(bs * query.shape[1], C)
+        feat = value.to(torch.float16).permute(2, 0, 1, 3).reshape(bs * num_cams * l, C)
+        if not fused_layer.supported(q2, feat, vis, da.num_heads, da.num_points, l):
+            return None
+        first, last, last_drop = ffn.layers[0], ffn.layers[1], ffn.layers[2]
+        n1, n2 = self.norms[0], self.norms[1]
+        cfg = dict(NH=da.num_heads, NP=da.num_points, Sh=int(hw[0]), Sw=int(hw[1]), training=self.training,
+                   p_attn=attn.dropout.p, p_ffn=first[2].p, p_out=last_drop.p, eps1=n1.eps, eps2=n2.eps)
+        params = (da.value_proj.weight, da.value_proj.bias, da.sampling_offsets.weight, da.sampling_offsets.bias,
+                  da.attention_weights.weight, da.attention_weights.bias, attn.output_proj.weight,
+                  attn.output_proj.bias, n1.weight, n1.bias, first[0].weight, first[0].bias, last.weight, last.bias,
+                  n2.weight, n2.bias)
+        out = fused_layer.voxel_layer(q2, feat, vis, cfg, params)
+        return out.view(bs, query.shape[1], C)
 
     def forward(self, query, key=None, value=None, bev_pos=None, query_pos=None, key_pos=None,
                 attn_masks=None, query_key_padding_mask=None, key_padding_mask=None, ref_2d=None,
                 ref_3d=None, bev_z=None, bev_h=None, bev_w=None, reference_points_cam=None, mask=None,
                 spatial_shapes=None, level_start_index=None, prev_bev=None, **kwargs):
+        fused = self._fused_layer_forward(query, value, query_pos, kwargs)
+        if fused is not None:
+            return fused
         norm_index = attn_index = ffn_index = 0
         identity = query
         if attn_masks is None:

@@ -286,7 +286,9 @@ def value_image(value, NH):
 
 
 VER_LAYOUT_TC_IMAGE = 2
-TC_FORWARD = 'sorted'    # 'sorted': sca_fwd_tc3_kernel on visibility-sorted rows; 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
+# 'sorted': visibility-sorted rows (sca_fwd_tc4_kernel, A operand in TMEM; sca_fwd_tc3_kernel for head dims it
+# does not cover); 'sorted3': force sca_fwd_tc3_kernel (debug / A-B timing); 'block': sca_fwd_tc_kernel (4x8x8 blocks)
+TC_FORWARD = 'sorted'
 
 
 class SCASampleTCFunction(Function):
@@ -312,8 +314,9 @@ class SCASampleTCFunction(Function):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if TC_FORWARD == 'sorted' and NP % 4 == 0 and logits.shape[1] % 4 == 0:
+        if TC_FORWARD in ('sorted', 'sorted3') and NP % 4 == 0 and logits.shape[1] % 4 == 0:
             order, smask, tile_union = vis.order
+            lib.ver_debug_sorted_variant(3 if TC_FORWARD == 'sorted3' else 0)
             check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
                                              _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw,
                                              NH, Dh, NP, _stream()))
@@ -438,7 +441,7 @@ class DropoutAddLayerNormFunction(Function):
         dgp = torch.empty((nb, C), dtype=torch.float32, device=z.device)
         dbp = torch.empty((nb, C), dtype=torch.float32, device=z.device)
         check(lib.ver_dropout_add_layernorm_bwd(_code(z.dtype), _ptr(dy), _ptr(z), _ptr(stats), _ptr(w32),
-                                                _ptr(dx), _ptr(dres), _ptr(dgp), _ptr(dbp), rows, C, ctx.p,
+                                                _ptr(dx), _ptr(dres), _ptr(dgp), _ptr(dbp), None, rows, C, ctx.p,
                                                 ctx.seed, _stream()))
         return dx, dres, dgp.sum(0).to(ctx.wdtype), dbp.sum(0).to(ctx.wdtype), None, None, None
 
@@ -467,7 +470,8 @@ class ReluDropoutFunction(Function):
         h, = ctx.saved_tensors
         dh = _c(dh, h.dtype)
         da = torch.empty_like(h)
-        check(lib.ver_relu_dropout_bwd(_code(h.dtype), _ptr(dh), _ptr(h), _ptr(da), h.numel(), ctx.p, _stream()))
+        check(lib.ver_relu_dropout_bwd(_code(h.dtype), _ptr(dh), _ptr(h), _ptr(da), h.numel(), ctx.p, 0, None,
+                                       _stream()))
         return da, None, None
 
 
