@@ -259,7 +259,7 @@ def run_b200(args):
         roof = None
         if sampler_ms:
             ach = bytes_min / (sampler_ms * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': 'sca_fwd_tc3_kernel<96> (tcgen05 fused SCA sampler forward, visibility-sorted rows)',
+            roof = {'bound': 'hbm', 'kernel': 'sca_fwd_tc4_kernel<96, 8> (tcgen05 fused SCA sampler forward, visibility-sorted rows, A operand in TMEM)',
                     'achieved': round(ach, 1),
                     'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'traffic': None,
                     'peak_source': peak_src, 'launch_ms': round(sampler_ms, 4),

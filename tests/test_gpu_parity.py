@@ -289,6 +289,87 @@ def test_training_gradients_vs_oracle_autograd():
     assert checked >= 30
 
 
+
+def test_fused_layer_fp16_gradients():
+    """fp16 storage training step: the one-node encoder layer (fused_layer.py, hand-written backward) against
+    (a) the module-by-module autograd path on the same fp16 kernels and (b) torch autograd on the fp64 CPU oracle.
+    Tolerances are fp16 ones (max-norm relative): 1e-2 between the two GPU paths (they round at different
+    places: weight gradients are written in fp32 by the fused node), 3e-2 against the oracle."""
+    from vln_ver_b200.modules.voxel_encoder import VoxelFormerLayer
+    grid, ncam, B, C = (4, 8, 8), 18, 2, 256
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=19)
+    feats = torch.from_numpy(synth.make_features(B, ncam, dim=C, seed=20))
+    l2i, sh = torch.from_numpy(l2i), torch.from_numpy(sh)
+
+    LS = 16384.0
+
+    def run(fuse):
+        head = make_head(grid, ncam, C=C, num_layers=2, occ_dims=32)
+        gts = [torch.from_numpy(x) for x in synth.make_occ_gt(B, head.voxel_num, frac=0.2)]
+        head = head.to(DEV).train()
+        V.set_compute_dtype(head, torch.float16)
+        used = []
+        for m in head.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if isinstance(m, VoxelFormerLayer):
+                m.fuse_layer = fuse
+                used.append(m)
+        n0 = V.launch_count()
+        outs = head(cuda(feats), None, lidar2img=cuda(l2i), originshift=cuda(sh))
+        loss = head.loss_only_occupancy(None, None, None, [cuda(t) for t in gts], None, outs)['loss_occupancy']
+        (loss * LS).backward()       # loss scaling as in fp16 training: keeps the small activation gradients normal
+        assert V.launch_count() > n0 and len(used) == 2
+        return head, loss.item(), {n: p.grad.float().cpu() / LS for n, p in head.named_parameters()
+                                   if p.grad is not None}, gts
+
+    head, loss_f, g_fused, gts = run(True)
+    _, loss_u, g_unfused, _ = run(False)
+    assert abs(loss_f - loss_u) < 2e-3 * abs(loss_u)
+    # oracle
+    sd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in head.state_dict().items()}
+    bev = ver_ref.get_voxel_features(sd, 'transformer.', feats.double(), sd['voxel_embedding.weight'],
+                                     *grid, PC, l2i, sh, num_layers=2)
+    occ = ver_ref.occ_head(sd, '', bev, *grid, head.occ_xdim, head.occ_ydim, head.occ_zdim,
+                           occ_dims=32, refine_occ=False, only_occ=True)
+    loss_ref = ver_ref.occupancy_loss(occ, gts)
+    loss_ref.backward()
+    assert abs(loss_f - loss_ref.item()) < 4e-3 * abs(loss_ref.item())
+    # every parameter gradient of BOTH GPU paths against the oracle.  This model is tiny (256 voxels x 2 panoramas),
+    # so gradients that sum signed per-voxel terms are noisy under fp16 storage in either path (measured: both
+    # paths sit 5-11 % from the fp64 oracle on the FFN's first Linear and agree with each other no better): 6e-2
+    # by default, 1.5e-1 for the cancellation-heavy ones; a wiring error shows up as O(1)
+    checked, bad = 0, []
+    for n, g in g_fused.items():
+        gref = sd[n].grad
+        if gref is None or gref.abs().max() < 1e-12:
+            continue
+        assert n in g_unfused, n
+        loose = any(k in n for k in ('level_embeds', 'cams_embeds', 'sampling_offsets', 'attention_weights',
+                                     'ffns.0.layers.0.0'))
+        tol = 1.5e-1 if loose else 6e-2
+        ef, eu, ed = rel_err(g, gref), rel_err(g_unfused[n], gref), rel_err(g, g_unfused[n])
+        if not (ef < tol and eu < tol and ed < 2 * tol):
+            bad.append(f'{n}: fused-oracle {ef:.2e} unfused-oracle {eu:.2e} fused-unfused {ed:.2e} (tol {tol})')
+        checked += 1
+    assert not bad, '\n'.join(bad)
+    assert checked >= 30
+
+
+def test_fused_layer_dropout_runs_and_is_finite():
+    """dropout p = 0.1 (vocc.py) through the fused node: finite loss / gradients, masks differ between steps."""
+    grid, ncam, B, C = (4, 8, 8), 18, 1, 256
+    head = make_head(grid, ncam, C=C, num_layers=2, occ_dims=32).to(DEV).train()
+    V.set_compute_dtype(head, torch.float16)
+    l2i, sh = synth.make_rig(B, ncam, grid, seed=23)
+    feats = cuda(torch.from_numpy(synth.make_features(B, ncam, dim=C, seed=24)))
+    l2i, sh = cuda(torch.from_numpy(l2i)), cuda(torch.from_numpy(sh))
+    outs1 = head(feats, None, lidar2img=l2i, originshift=sh)['bev_embed']
+    outs2 = head(feats, None, lidar2img=l2i, originshift=sh)['bev_embed']
+    assert torch.isfinite(outs1).all() and not torch.equal(outs1, outs2)
+    outs1.float().square().mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in head.parameters() if p.grad is not None)
+
 def test_focal_loss_vs_oracle():
     torch.manual_seed(1)
     N = 5000
@@ -405,10 +486,30 @@ def test_visibility_order_properties():
                 assert (int(tu[b, t]) & 0xffffffff) == u
 
 
+def _offset_grad_comparable(rpc, mask, logits, B, ncam, Nq, NH, NP=8, S=14, eps=2e-4):
+    """(B*Nq, 192) bool: False for the offset entries of (voxel, head, point) whose sampling coordinate in some
+    camera that sees the voxel lies within `eps` pixels of an integer."""
+    off = logits[:, :NH * NP * 2].double().view(B, Nq, NH, NP, 2)
+    ok = torch.ones(B, Nq, NH, NP, dtype=torch.bool)
+    for cam in range(ncam):
+        ref = rpc[cam, :, :, 0, :].double()                                  # (B, Nq, 2)
+        xy = (ref[:, :, None, None, :] + off / S) * S - 0.5
+        near = ((xy - xy.round()).abs() < eps).any(-1)                        # (B, Nq, NH, NP)
+        ok &= ~(near & mask[cam, :, :, 0][:, :, None, None])
+    full = torch.ones(B * Nq, logits.shape[1], dtype=torch.bool)
+    full[:, :NH * NP * 2] = ok[..., None].expand(B, Nq, NH, NP, 2).reshape(B * Nq, NH * NP * 2)
+    return full
+
+
 @pytest.mark.parametrize('fwd', ['sorted', 'sorted3', 'block'])
 @pytest.mark.parametrize('Dh,grid,B', [(96, (8, 20, 20), 2), (32, (3, 5, 7), 2), (64, (4, 8, 8), 1), (96, (3, 11, 13), 3)])
 def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B, fwd, monkeypatch):
+    from vln_ver_b200._lib import lib as _l
     monkeypatch.setattr(ops, 'TC_FORWARD', fwd)
+    # the voxel-block forward variant is paired with the first-generation backward kernel, the sorted ones with
+    # the current one, so that every tensor-core kernel keeps its parity test
+    _l.ver_debug_bwd_variant.argtypes = [__import__('ctypes').c_int]
+    _l.ver_debug_bwd_variant(1 if fwd == 'block' else 0)
     ncam, NH = 18, 8
     Nq = grid[0] * grid[1] * grid[2]
     l2i, sh = synth.make_rig(B, ncam, grid, seed=11)
@@ -431,7 +532,14 @@ def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B, fwd, monkeypatch):
     assert rel_err(out, ref) < 1e-3
     out.backward(cuda(gout))
     assert rel_err(vc.grad, gv_r) < 2e-3
-    assert rel_err(lc.grad, gl_r) < 2e-3
+    # d/d(offset) is discontinuous where a sampling coordinate crosses a pixel centre line; implementations
+    # that round the coordinate differently (the kernels use ref * W + 0.5 + offset, the oracle grid_sample's
+    # chain) may legitimately sit on opposite sides when it is within rounding error of one: such entries
+    # (about one in 10^6) are excluded from the comparison
+    safe = _offset_grad_comparable(rpc.cpu(), mask.cpu(), logits, B, ncam, Nq, NH)
+    assert safe.float().mean() > 0.999
+    assert rel_err(lc.grad.cpu() * safe, gl_r * safe) < 2e-3
+    _l.ver_debug_bwd_variant(0)
     # and the gather kernels agree with it
     out_g = ops.sca_sample(cuda(value).view(B * ncam, 196, NH, Dh), cuda(logits), vis, 14, 14, NH, 8)
     assert rel_err(out, out_g) < 1e-3

@@ -94,6 +94,59 @@ def main():
     _lib.lib.ver_debug_sorted_variant(0)
     if '--fwd-only' in sys.argv:
         return
+    # ---- backward: sca_bwd_tc2_kernel (two threads per hit, lane-interleaved Dots staging) vs sca_bwd_tc_kernel
+    names_b2 = {16: 'un-tap + hit ids', 18: "A' rows (+ G gather latency)", 17: 'G image stores',
+                19: 'fences, MMA issue, Dots MMAs', 20: 'Dots dump', 21: 'tap read-back, softmax bwd, atomics',
+                23: 'wait dV^T MMAs', 22: 'dV^T -> grad_value'}
+    _lib.lib.ver_debug_bwd_variant.restype = ctypes.c_int
+    _lib.lib.ver_debug_bwd_variant.argtypes = [ctypes.c_int]
+    counts, index = vis.index
+    gs = torch.randn(B, Nq, NH * Dh, device='cuda', generator=g).half()
+    gvalue = torch.empty(B * ncam, 196, NH * Dh, device='cuda')
+    glogits = torch.empty_like(logits)
+
+    def launch_bwd():
+        _lib.check(_lib.lib.ver_sca_backward(_lib.VER_F16, vimg.data_ptr(), ops.VER_LAYOUT_TC_IMAGE, logits.data_ptr(), 192,
+                                             rpc.data_ptr(), bits.data_ptr(), counts.data_ptr(), index.data_ptr(),
+                                             gs.data_ptr(), gvalue.data_ptr(), glogits.data_ptr(), B, ncam, *grid, 14, 14,
+                                             NH, Dh, 8, torch.cuda.current_stream().cuda_stream))
+    ref_b = None
+    for variant, kname in ((0, 'sca_bwd_tc2_kernel'), (1, 'sca_bwd_tc_kernel')):
+        _lib.lib.ver_debug_bwd_variant(variant)
+        for _ in range(2):
+            launch_bwd()
+        torch.cuda.synchronize()
+        if ref_b is None:
+            ref_b = (gvalue.clone(), glogits.clone())
+        else:
+            dv = (gvalue - ref_b[0]).abs().max().item() / ref_b[0].abs().max().item()
+            dl = (glogits - ref_b[1]).abs().max().item() / ref_b[1].abs().max().item()
+            print(f'  max-norm difference old vs new backward: grad_value {dv:.2e}, grad_logits {dl:.2e}')
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ts = []
+        for i in range(8):
+            flush.zero_()
+            ev[0].record()
+            launch_bwd()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ts.append(ev[0].elapsed_time(ev[1]))
+        ts.sort()
+        print(f'{kname} alone (L2 flushed, includes the glogits memset): median {ts[4] * 1e3:.1f} us, min {ts[0] * 1e3:.1f} us')
+        if variant == 0:
+            fb = hook('ver_debug_bwd2_timing')
+            assert fb(1, None) == 0
+            launch_bwd()
+            torch.cuda.synchronize()
+            outb = (ctypes.c_ulonglong * 32)()
+            assert fb(0, outb) == 0
+            bc = B * ncam * NH
+            print(f'  {bc} CTAs, cycles per CTA (thread 0):')
+            for i in (16, 18, 17, 19, 20, 21, 23, 22):
+                print(f'  [{i:2d}] {names_b2[i]:42s} {outb[i] / bc:10.0f}')
+    _lib.lib.ver_debug_bwd_variant(0)
+    if '--no-legacy' in sys.argv:
+        return
     ops.TC_FORWARD = 'block'
     fn = _lib.lib.ver_debug_tc_timing
     fn.restype = ctypes.c_int

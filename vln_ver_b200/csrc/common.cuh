@@ -42,6 +42,12 @@ int ver_sca_backward_tc(const void* vimg, const float* logits, int ld, const flo
                         const int32_t* counts, const int32_t* index, const void* gslots, float* gvalue,
                         float* glogits, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
                         cudaStream_t st);
+// second-generation tensor-core backward, sca_bwd_tc2.cu
+int ver_bwd_tc2_supported(int Ncam, int Sh, int Sw, int Dh, int NP, int ld);
+int ver_sca_backward_tc2(const void* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
+                         const int32_t* counts, const int32_t* index, const void* gslots, float* gvalue,
+                         float* glogits, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
+                         cudaStream_t st);
 // TMEM-operand sorted-row forward, sca_tc4.cu
 int ver_tc4_supported(int Ncam, int S, int Dh, int NP);
 int ver_sca_forward_tc4(const void* vimg, const float* logits, int ld, const float* rpc, const int32_t* order,

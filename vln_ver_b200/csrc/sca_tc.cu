@@ -802,10 +802,20 @@ int ver_sca_forward_tc(const void* vimg, const float* logits, int ld, const floa
 #undef FWD
 }
 
+// debug: 0 = newest backward kernel that covers the shape (default), 1 = force sca_bwd_tc_kernel
+static int g_bwd_variant = 0;
+extern "C" int ver_debug_bwd_variant(int v) {
+    g_bwd_variant = v;
+    return VER_OK;
+}
+
 int ver_sca_backward_tc(const void* vimg, const float* logits, int ld, const float* rpc, const uint32_t* vis_bits,
                         const int32_t* counts, const int32_t* index, const void* gslots, float* gvalue,
                         float* glogits, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
                         cudaStream_t st) {
+    if (g_bwd_variant != 1 && ver_bwd_tc2_supported(Ncam, Sh, Sw, Dh, NP, ld))
+        return ver_sca_backward_tc2(vimg, logits, ld, rpc, vis_bits, counts, index, gslots, gvalue, glogits, B, Ncam,
+                                    Nq, Sh, Sw, NH, Dh, NP, st);
     const int SP = (Sh * Sw + 15) / 16 * 16;
 #define BWD(D) launch_bwd_tc<D>((const __half*)vimg, logits, ld, rpc, vis_bits, counts, index, (const __half*)gslots, gvalue, glogits, B, Ncam, Nq, Sh, Sw, SP, NH, NP, st)
     switch (Dh) {

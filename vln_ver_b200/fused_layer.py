@@ -99,12 +99,16 @@ def _cast_colsum(x32):
     return y, _fold(part, C)
 
 
-def supported(q, feat, vis, NH, NP, S):
+def supported(q, feat, vis, NH, NP, S, F):
+    """F: hidden width of the FFN.  The column-sum kernels need C / 8, F / 8 and NH * NP * 3 / 8 to divide their
+    thread count (ver_colsum_partial_rows)."""
     C = q.shape[-1]
+    n_part = lib.ver_colsum_partial_rows()
+    L = NH * NP * 3
     return (q.is_cuda and q.dtype == torch.float16 and feat.dtype == torch.float16 and vis is not None
-            and vis.bits is not None and C % 8 == 0 and C <= 1024 and NP % 4 == 0 and (NH * NP * 3) % 4 == 0
+            and vis.bits is not None and C % 8 == 0 and C <= 1024 and NP % 4 == 0 and L % 8 == 0 and F % 8 == 0
             and ops.tc_supported(torch.float16, vis.rpc.shape[0], S, C // NH, NP)
-            and (lib.ver_colsum_partial_rows() % (C // 8) == 0))
+            and n_part % (C // 8) == 0 and n_part % (F // 8) == 0 and n_part % (L // 8) == 0)
 
 
 class VoxelLayerFunction(Function):

@@ -215,9 +215,9 @@ class VoxelFormerLayer(MyCustomBaseTransformerLayer):
             return None
         q2 = query.to(torch.float16).reshape(bs * query.shape[1], C)
         feat = value.to(torch.float16).permute(2, 0, 1, 3).reshape(bs * num_cams * l, C)
-        if not fused_layer.supported(q2, feat, vis, da.num_heads, da.num_points, l):
-            return None
         first, last, last_drop = ffn.layers[0], ffn.layers[1], ffn.layers[2]
+        if not fused_layer.supported(q2, feat, vis, da.num_heads, da.num_points, l, first[0].out_features):
+            return None
         n1, n2 = self.norms[0], self.norms[1]
         cfg = dict(NH=da.num_heads, NP=da.num_points, Sh=int(hw[0]), Sw=int(hw[1]), training=self.training,
                    p_attn=attn.dropout.p, p_ffn=first[2].p, p_out=last_drop.p, eps1=n1.eps, eps2=n2.eps)
