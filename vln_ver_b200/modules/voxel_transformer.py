@@ -104,7 +104,8 @@ class VoxelPerceptionTransformer(PrecisionMixin, BaseModule):
         if h * w != S:
             raise ValueError(f'{S} tokens per view is not a square map')
         cd = self.compute_dtype or torch.float32
-        bev_queries = bev_queries.unsqueeze(1).expand(-1, bs, -1)
+        # cast the (Nq, C) table once, THEN broadcast over the batch (the reference repeats, :137)
+        bev_queries = bev_queries.to(cd).unsqueeze(1).expand(-1, bs, -1)
         if bev_pos is not None:
             bev_pos = bev_pos.flatten(2).permute(2, 0, 1)
         feat = _FeatEmbed.apply(mlvl_feats, self.cams_embeds if self.use_cams_embeds else None,
