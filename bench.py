@@ -257,11 +257,16 @@ def run_b200(args):
         bytes_survey = (B * NCAM * 196 * EMBED * bv + P * (512 + 256) + P * 4
                         + B * Nq * EMBED * bv + B * Nq * 4)      # SURVEY.md 8(d) fused formula
         roof = None
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'sampler_traffic.json')
+        if os.path.exists(tpath) and args.batch == PER_GPU_BATCH and tuple(args.grid) == GRID:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
         if sampler_ms:
             ach = bytes_min / (sampler_ms * 1e-3) / 1e9
             roof = {'bound': 'hbm', 'kernel': 'sca_fwd_tc4_kernel<96, 8> (tcgen05 fused SCA sampler forward, visibility-sorted rows, A operand in TMEM)',
                     'achieved': round(ach, 1),
-                    'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'traffic': None,
+                    'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'traffic': traffic, 'traffic_source': traffic_src,
                     'peak_source': peak_src, 'launch_ms': round(sampler_ms, 4),
                     'algorithmic_bytes': int(bytes_min),
                     'achieved_survey_formula': round(bytes_survey / (sampler_ms * 1e-3) / 1e9, 1),
