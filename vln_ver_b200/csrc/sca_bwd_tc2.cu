@@ -73,6 +73,28 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// loads the compiler may not sink to their first use (the software pipeline relies on their issue position)
+__device__ __forceinline__ float4 ldg_pin(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_pin(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ldg_pin(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_pin(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // tent weight of a cell at signed distance d, and its derivative with respect to the coordinate
 __device__ __forceinline__ float tent(float d) { return fmaxf(1.f - fabsf(d), 0.f); }
 // (cell to the left of / at the coordinate: -1 on [0, 1); cell to the right: +1 on [-1, 0) -- the reference's
@@ -99,9 +121,29 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
     __shared__ __align__(8) uint64_t bar_v, bar_dots, bar_dv;
     __shared__ uint32_t s_tmem;
 
-    const int bv = blockIdx.y, h = blockIdx.x;
-    const int b = bv / Ncam, cam = bv % Ncam;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = blockIdx.x;
+    // longest-processing-time-first: CTA y takes the view with the y-th largest hit count, so that the last
+    // (partial) wave of the 1-CTA-per-SM grid holds the cheapest views.  Every CTA ranks the views itself
+    // (n^2 / 256 L1-resident loads per thread, n = B * Ncam); skipped for very large batches.
+    __shared__ int s_bv;
+    const int nviews = B * Ncam;
+    if (nviews <= 512) {
+        for (int v = tid; v < nviews; v += kB2Threads) {
+            const int c = counts[v];
+            int rank = 0;
+            for (int u = 0; u < nviews; ++u) {
+                const int cu = counts[u];
+                rank += (cu > c || (cu == c && u < v)) ? 1 : 0;
+            }
+            if (rank == (int)blockIdx.y) s_bv = v;
+        }
+    } else if (tid == 0) {
+        s_bv = blockIdx.y;
+    }
+    __syncthreads();
+    const int bv = s_bv;
+    const int b = bv / Ncam, cam = bv % Ncam;
 
     if (tid == 0) {
         mbar_init(&bar_v, 1);
@@ -153,12 +195,12 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         if (n < 0) return;
         const float* row = logits + ((size_t)b * Nq + n) * ld;
 #pragma unroll
-        for (int i = 0; i < NP / 4; ++i) d.lg4[i] = __ldg(reinterpret_cast<const float4*>(row + NH * NP * 2 + h * NP + i * 4));
+        for (int i = 0; i < NP / 4; ++i) d.lg4[i] = ldg_pin(reinterpret_cast<const float4*>(row + NH * NP * 2 + h * NP + i * 4));
 #pragma unroll
         for (int i = 0; i < PPT / 2; ++i)
-            d.off4[i] = __ldg(reinterpret_cast<const float4*>(row + h * NP * 2 + half * PPT * 2 + i * 4));
-        d.ref = __ldg(rp + n);
-        d.bits = __ldg(vis_bits + (size_t)b * Nq + n);
+            d.off4[i] = ldg_pin(reinterpret_cast<const float4*>(row + h * NP * 2 + half * PPT * 2 + i * 4));
+        d.ref = ldg_pin(rp + n);
+        d.bits = ldg_pin(vis_bits + (size_t)b * Nq + n);
     };
     constexpr int kG = (kB2Hits * CG + kB2Threads - 1) / kB2Threads;
     auto load_g = [&](const int* sn, uint4 (&gv)[kG]) {
@@ -169,8 +211,8 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             if (i < kB2Hits * CG) {
                 const int n = sn[i / CG];
                 if (n >= 0)
-                    gv[u] = __ldg(reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH +
-                                                                 (i % CG) * 8));
+                    gv[u] = ldg_pin(reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH +
+                                                                   (i % CG) * 8));
             }
         }
     };
@@ -199,10 +241,14 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         }
         if (tid < kB2Hits) {
             sn_next[tid] = sn_pref;                  // loaded one chunk ago
-            sn_pref = base + 2 * kB2Hits + tid < nitems ? idx[base + 2 * kB2Hits + tid] : -1;
+            sn_pref = base + 2 * kB2Hits + tid < nitems
+                          ? (int)ldg_pin(reinterpret_cast<const uint32_t*>(idx + base + 2 * kB2Hits + tid))
+                          : -1;
         }
         load_row(n_nx, d_nx);
-        const int n_n2 = base + 2 * kB2Hits + r < nitems ? idx[base + 2 * kB2Hits + r] : -1;
+        const int n_n2 = base + 2 * kB2Hits + r < nitems
+                             ? (int)ldg_pin(reinterpret_cast<const uint32_t*>(idx + base + 2 * kB2Hits + r))
+                             : -1;
         tb.lap(16);                                  // un-tap + prefetch issue
         // ---- my hit: softmax over all points (both threads of the pair compute it), then my PPT points
         const int n = n_cur;
