@@ -112,3 +112,23 @@ def test_reference_point_grid_matches_oracle_bit_for_bit():
     from oracle import ver_ref
     a = V.VoxelFormerEncoder.get_reference_points(4, 15, 15, dim='3d', bs=2, device='cpu')
     assert torch.equal(a, ver_ref.get_reference_points_3d(4, 15, 15, bs=2))
+
+
+def test_half_cache_follows_parameter_versions():
+    """fused_layer.half_of: one fp16 copy per optimizer step -- refreshed when the parameter is updated in place
+    (optimizer.step bumps _version) or replaced, reused otherwise; concatenations follow all their parts."""
+    from vln_ver_b200 import fused_layer as F
+    a = torch.nn.Parameter(torch.randn(4, 8))
+    b = torch.nn.Parameter(torch.randn(2, 8))
+    h1 = F.half_of(a)
+    assert h1.dtype == torch.float16 and F.half_of(a) is h1
+    cat1 = F.half_of(a, b)
+    assert cat1.shape == (6, 8) and F.half_of(a, b) is cat1
+    with torch.no_grad():
+        a.add_(1.0)
+    h2 = F.half_of(a)
+    assert h2 is not h1 and torch.equal(h2, a.detach().half())
+    cat2 = F.half_of(a, b)
+    assert cat2 is not cat1 and torch.equal(cat2[:4], a.detach().half())
+    f = F.f32_cat(a, b)
+    assert f.dtype == torch.float32 and F.f32_cat(a, b) is f

@@ -545,6 +545,56 @@ def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B, fwd, monkeypatch):
     assert rel_err(out, out_g) < 1e-3
 
 
+
+# ------------------------------------------------------------------ column-sum (bias gradient) kernels
+@pytest.mark.parametrize('C,p', [(768, 0.0), (768, 0.1), (256, 0.1), (128, 0.0)])
+def test_layernorm_backward_column_sums(C, p):
+    """ver_dropout_add_layernorm_bwd's optional third partial (column sums of dx = bias gradient of the Linear
+    in front) equals dx.sum(0) of what the kernel stored; dgamma / dbeta unchanged by asking for it."""
+    from vln_ver_b200 import fused_layer as F
+    rows = 5000
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(rows, C, device=DEV, generator=g).half()
+    res = torch.randn(rows, C, device=DEV, generator=g).half()
+    dy = torch.randn(rows, C, device=DEV, generator=g).half()
+    gam = torch.rand(C, device=DEV, generator=g) + 0.5
+    bet = torch.randn(C, device=DEV, generator=g)
+    y, z, st = F._ln_fwd(x, res, gam, bet, p, 1e-5, 77, True)
+    dx, dres, dgam, dbet, dxs = F._ln_bwd(dy, z, st, gam, p, 77)
+    assert rel_err(dxs, dx.float().sum(0)) < 1e-5
+    # against torch autograd on the same (fp16-rounded) inputs, the mask taken from the kernel's own forward
+    keep = None
+    if p > 0:
+        _, z0, _ = F._ln_fwd(x, None, gam, bet, p, 1e-5, 77, True)       # z0 = dropout(x)
+        keep = (z0 != 0) | (x == 0)
+    xr = x.float().requires_grad_(True)
+    rr = res.float().requires_grad_(True)
+    gr = gam.clone().requires_grad_(True)
+    br = bet.clone().requires_grad_(True)
+    xd = xr if keep is None else xr * keep / (1 - p)
+    zz = (rr + xd).half().float() + ((rr + xd) - (rr + xd).detach())      # value rounded like the kernel, grad exact
+    torch.nn.functional.layer_norm(zz, (C,), gr, br, 1e-5).backward(dy.float())
+    assert rel_err(dx, xr.grad) < 2e-3 and rel_err(dres, rr.grad) < 2e-3
+    assert rel_err(dgam, gr.grad) < 2e-3 and rel_err(dbet, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize('C', [192, 768, 1536])
+def test_cast_colsum_and_relu_backward_colsum(C):
+    from vln_ver_b200 import fused_layer as F
+    rows = 3001
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x32 = torch.randn(rows, C, device=DEV, generator=g)
+    y16, cs = F._cast_colsum(x32)
+    assert torch.equal(y16, x32.half())
+    assert rel_err(cs, x32.sum(0)) < 1e-5
+    h = torch.relu(torch.randn(rows, C, device=DEV, generator=g)).half()
+    dh = torch.randn(rows, C, device=DEV, generator=g).half()
+    ref = torch.where(h > 0, dh.float() / 0.9, torch.zeros((), device=DEV)).half()
+    da = dh.clone()
+    cs2 = F._relu_dropout_bwd_(da, h, 0.1)
+    assert rel_err(da, ref) < 1e-3
+    assert rel_err(cs2, da.float().sum(0)) < 1e-5
+
 # ------------------------------------------------------------------ size-independent properties
 def test_full_size_properties():
     """BASELINE config-2/3 shape (18 views, 16x40x40): linearity of the sampler in `value`,
