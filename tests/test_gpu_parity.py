@@ -572,7 +572,7 @@ def test_layernorm_backward_column_sums(C, p):
     gr = gam.clone().requires_grad_(True)
     br = bet.clone().requires_grad_(True)
     xd = xr if keep is None else xr * keep / (1 - p)
-    zz = (rr + xd).half().float() + ((rr + xd) - (rr + xd).detach())      # value rounded like the kernel, grad exact
+    zz = (rr + xd).half().float().detach() + ((rr + xd) - (rr + xd).detach())      # value rounded like the kernel, grad exact
     torch.nn.functional.layer_norm(zz, (C,), gr, br, 1e-5).backward(dy.float())
     assert rel_err(dx, xr.grad) < 2e-3 and rel_err(dres, rr.grad) < 2e-3
     assert rel_err(dgam, gr.grad) < 2e-3 and rel_err(dbet, br.grad) < 2e-3
