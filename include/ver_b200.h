@@ -104,6 +104,27 @@ int ver_msda_backward(int dtype, const void* value, const int32_t* shapes_hw, in
                       float* grad_w, int Bv, int S, int NH, int Dh, int Nq, int NP,
                       ver_stream_t stream);
 
+/* ---------------------------------------------------------------- N2 / N3: 3-D sampler
+ * Replaces voxel_multi_scale_deformable_attn_pytorch (M/voxel_temporal_self_attention.py:275-335)
+ * as called by VoxelCustomMSDeformableAttention.forward (M/voxel_decoder.py:315-316) and
+ * VoxelTemporalSelfAttention.forward (M/voxel_temporal_self_attention.py:256).
+ *   value  [Bv, S, NH, Dh] dtype, S = sum_l d_l*h_l*w_l, voxel index (d*h_l + y)*w_l + x
+ *   shapes_dhw host int32 [NL,3] = (d,h,w)
+ *   loc    [Bv, Nq, NH, NL, NP, 3] fp32 (x,y,z) in [0,1]   w [Bv, Nq, NH, NL, NP] fp32
+ *   out    [Bv, Nq, NH*Dh] dtype
+ * trilinear, zero padding, align_corners=False (voxel coordinate = loc*size - 0.5); Dh <= 256. */
+int ver_msda3d_forward(int dtype, const void* value, const int32_t* shapes_dhw, int NL, const float* loc,
+                       const float* w, void* out, int Bv, int S, int NH, int Dh, int Nq, int NP,
+                       ver_stream_t stream);
+
+/* Gradient of ver_msda3d_forward (the reference differentiates through F.grid_sample).
+ *   grad_out [Bv, Nq, NH*Dh] dtype
+ *   grad_value [Bv, S, NH, Dh] fp32, grad_loc like loc, grad_w like w: all three are OVERWRITTEN. */
+int ver_msda3d_backward(int dtype, const void* value, const int32_t* shapes_dhw, int NL, const float* loc,
+                        const float* w, const void* grad_out, float* grad_value, float* grad_loc,
+                        float* grad_w, int Bv, int S, int NH, int Dh, int Nq, int NP,
+                        ver_stream_t stream);
+
 /* ---------------------------------------------------------------- A3 (+) A4 (+) A5 fused
  * The sampling part of SpatialCrossAttention.forward (M/spatial_cross_attention.py:138-173)
  * with MSDeformableAttention3D's softmax / location arithmetic (:340-374) fused in, for

@@ -342,6 +342,210 @@ def gen_head():
     print('head ok')
 
 
+# --------------------------------------------------------------------------- N2 / N3
+DEC_C, DEC_GRID, DEC_NQ, DEC_BS, DEC_LAYERS = 64, (4, 6, 6), 10, 2, 2
+
+
+def decoder_cfg(C, num_layers):
+    """vocc.py:137-158 at a small width."""
+    return dict(
+        type='VoxelDetectionTransformerDecoder', num_layers=num_layers, return_intermediate=True,
+        transformerlayers=dict(
+            type='DetrTransformerDecoderLayer',
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=8, dropout=0.1),
+                       dict(type='VoxelCustomMSDeformableAttention', embed_dims=C, num_levels=1)],
+            ffn_cfgs=dict(type='FFN', embed_dims=C, feedforward_channels=1024, num_fcs=2, ffn_drop=0.,
+                          act_cfg=dict(type='ReLU', inplace=True)),
+            feedforward_channels=2 * C, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))
+
+
+def randomize(module, seed):
+    """every weight matrix xavier-uniform, every bias / 1-D parameter small random: nothing on the
+    decoder path may stay at a zero init, or the fixture would not exercise it."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() > 1:
+                bound = (6.0 / (p.shape[0] + p.shape[1])) ** 0.5
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
+            elif name.endswith('sampling_offsets.bias') or 'norms' in name and name.endswith('weight'):
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+
+
+def gen_msda3d():
+    vtsa = mmcv_shim.import_reference('bevformer.modules.voxel_temporal_self_attention')
+    ref3d = vtsa.voxel_multi_scale_deformable_attn_pytorch
+    g = torch.Generator().manual_seed(71)
+    out = {}
+    for name, (Bv, shapes, NH, Dh, Nq, NP) in {
+            'small': (3, [(3, 5, 7)], 4, 8, 13, 4),
+            'dh96': (2, [(4, 6, 6)], 8, 96, 9, 4),
+            'two_level': (2, [(3, 4, 5), (2, 2, 3)], 2, 40, 7, 3)}.items():
+        NL = len(shapes)
+        S = sum(d * h * w for d, h, w in shapes)
+        D, H, W = shapes[0]
+        value = torch.randn(Bv, S, NH, Dh, generator=g)
+        loc = torch.rand(Bv, Nq, NH, NL, NP, 3, generator=g) * 1.6 - 0.3
+        loc[0, 0, 0, 0, 0] = torch.tensor([0.0, 0.0, 0.0])                 # corner of the padded volume
+        loc[0, 0, 0, 0, 1] = torch.tensor([1.0, 1.0, 1.0])
+        loc[0, 0, 0, 0, 2] = torch.tensor([0.5 / W, 0.5 / H, 0.5 / D])     # centre of voxel (0,0,0)
+        loc[0, 1, 0, 0, 0] = torch.tensor([-3.0, 7.0, 0.5])                # far outside
+        w = torch.rand(Bv, Nq, NH, NL, NP, generator=g)
+        w = w / w.sum((-1, -2), keepdim=True)
+        gout = torch.randn(Bv, Nq, NH * Dh, generator=g)
+        v64 = value.double().requires_grad_(True)
+        l64 = loc.double().requires_grad_(True)
+        w64 = w.double().requires_grad_(True)
+        ss = torch.tensor(shapes)
+        y = ref3d(v64, ss, l64, w64)
+        gv, gl, gw = torch.autograd.grad(y, (v64, l64, w64), gout.double())
+        v2 = value.double().requires_grad_(True)
+        y2 = ver_ref.voxel_multi_scale_deformable_attn_pytorch(v2, ss, l64, w64)
+        assert torch.equal(y, y2)
+        out.update({f'{name}.value': value.numpy(), f'{name}.loc': loc.numpy(), f'{name}.w': w.numpy(),
+                    f'{name}.gout': gout.numpy(), f'{name}.shapes': np.array(shapes),
+                    f'{name}.out': y.detach().numpy(), f'{name}.gvalue': gv.numpy(),
+                    f'{name}.gloc': gl.numpy(), f'{name}.gw': gw.numpy()})
+    np.savez_compressed(os.path.join(OUT, 'msda3d_cases.npz'), **out)
+    print('msda3d ok')
+
+
+def gen_decoder():
+    """Unmodified VoxelCustomMSDeformableAttention, VoxelDetectionTransformerDecoder (on the shim's
+    MultiheadAttention + a DetrTransformerDecoderLayer that subclasses the reference's own copy of
+    BaseTransformerLayer) and VoxelTemporalSelfAttention (with a sampling_offsets bias of the Linear's
+    own size, see ver_ref.temporal_self_attention_forward)."""
+    vd = mmcv_shim.import_reference('bevformer.modules.voxel_decoder')
+    vtsa = mmcv_shim.import_reference('bevformer.modules.voxel_temporal_self_attention')
+    mmcv_shim.register_detr_decoder_layer()
+    C, grid, nq, bs, L = DEC_C, DEC_GRID, DEC_NQ, DEC_BS, DEC_LAYERS
+    Nv = grid[0] * grid[1] * grid[2]
+    ss = torch.tensor([list(grid)])
+    g = torch.Generator().manual_seed(81)
+    out = {}
+
+    # -- the attention module alone
+    attn = vd.VoxelCustomMSDeformableAttention(embed_dims=C, num_levels=1, batch_first=False).eval()
+    randomize(attn, 82)
+    query = torch.randn(nq, bs, C, generator=g)
+    query_pos = torch.randn(nq, bs, C, generator=g) * 0.5
+    value = torch.randn(Nv, bs, C, generator=g)
+    ref = torch.rand(bs, nq, 1, 3, generator=g)
+    with torch.no_grad():
+        y = attn(query, key=None, value=value, query_pos=query_pos, reference_points=ref, spatial_shapes=ss,
+                 level_start_index=torch.tensor([0]))
+        y2 = ver_ref.voxel_custom_msda_forward(dict(attn.state_dict()), '', query, value, ref, ss,
+                                               query_pos=query_pos)
+    assert torch.allclose(y, y2, atol=1e-6), (y - y2).abs().max()
+    out.update({'attn.query': query.numpy(), 'attn.query_pos': query_pos.numpy(), 'attn.value': value.numpy(),
+                'attn.ref': ref.numpy(), 'attn.out': y.numpy(), 'grid': np.array(grid)})
+    out.update({f'attn.sd.{k}': v for k, v in sd_np(attn).items()})
+
+    # -- the decoder with box refinement
+    dec = mmcv_shim.build_transformer_layer_sequence(decoder_cfg(C, L)).eval()
+    randomize(dec, 83)
+    regs = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(C, C), torch.nn.ReLU(),
+                                                    torch.nn.Linear(C, 10)) for _ in range(L)]).eval()
+    randomize(regs, 84)
+    ref3 = torch.rand(bs, nq, 3, generator=g)
+    with torch.no_grad():
+        hs, refs = dec(query=query, key=None, value=value, query_pos=query_pos, reference_points=ref3,
+                       reg_branches=regs, cls_branches=None, spatial_shapes=ss,
+                       level_start_index=torch.tensor([0]))
+        hs2, refs2 = ver_ref.decoder_forward(dict(dec.state_dict()), '', query, value, query_pos, ref3, ss,
+                                             num_layers=L, reg_branches=regs)
+    assert torch.allclose(hs, hs2, atol=2e-6), (hs - hs2).abs().max()
+    assert torch.allclose(refs, refs2, atol=1e-6)
+    out.update({'dec.ref': ref3.numpy(), 'dec.hs': hs.numpy(), 'dec.refs': refs.numpy()})
+    out.update({f'dec.sd.{k}': v for k, v in sd_np(dec).items()})
+    out.update({f'reg.sd.{k}': v for k, v in sd_np(regs).items()})
+
+    # -- temporal self-attention (N3)
+    tsa = vtsa.VoxelTemporalSelfAttention(embed_dims=C, num_levels=1, batch_first=True).eval()
+    tsa.sampling_offsets.bias.data = torch.zeros(tsa.sampling_offsets.out_features)
+    randomize(tsa, 85)
+    vq = torch.randn(bs, Nv, C, generator=g)
+    vpos = torch.randn(bs, Nv, C, generator=g) * 0.5
+    zs, ys, xs = torch.meshgrid(*[(torch.arange(n) + 0.5) / n for n in grid], indexing='ij')
+    ref_vox = torch.stack((xs, ys, zs), -1).view(1, Nv, 1, 3).repeat(bs * 2, 1, 1, 1)
+    with torch.no_grad():
+        yt = tsa(vq, query_pos=vpos, reference_points=ref_vox, spatial_shapes=ss,
+                 level_start_index=torch.tensor([0]))
+        yt2 = ver_ref.temporal_self_attention_forward(dict(tsa.state_dict()), '', vq, ref_vox, ss, query_pos=vpos)
+    assert torch.allclose(yt, yt2, atol=1e-6), (yt - yt2).abs().max()
+    out.update({'tsa.query': vq.numpy(), 'tsa.query_pos': vpos.numpy(), 'tsa.ref': ref_vox.numpy(),
+                'tsa.out': yt.numpy()})
+    out.update({f'tsa.sd.{k}': v for k, v in sd_np(tsa).items()})
+    np.savez_compressed(os.path.join(OUT, 'decoder_c64.npz'), **out)
+    print('decoder ok')
+
+
+def gen_head_detection():
+    """Unmodified VoxelFormerOccupancyHead.forward, default branch (only_occ=False, HEAD:537-625), with the
+    transformer replaced by fixed outputs: pins the detection tail (cls / reg branches + box placement) and
+    the occupancy tail fed from the (Nq, bs, C) layout."""
+    for mod in ('voxel_positional_embedding', 'spatial_cross_attention', 'voxel_encoder', 'voxel_decoder',
+                'voxel_transformer'):
+        mmcv_shim.import_reference('bevformer.modules.' + mod)
+    hd = mmcv_shim.import_reference('bevformer.dense_heads.voxelformer_occupancy_head')
+    mmcv_shim.register_detr_decoder_layer()
+    C, grid, seed, nq, L = 32, (4, 6, 6), 91, 10, 2
+    torch.manual_seed(seed)
+    head = hd.VoxelFormerOccupancyHead(
+        bev_h=grid[1], bev_w=grid[2], bev_z=grid[0], num_query=nq, num_classes=17, in_channels=C,
+        sync_cls_avg_factor=True, with_box_refine=True, as_two_stage=False, point_cloud_range=PC,
+        occupancy_size=[2.0, 2.0, 0.5], occ_dims=16, occupancy_classes=16, only_occ=False, only_det=False,
+        refine_occ=False,
+        transformer=mmcv_shim.ConfigDict(
+            type='VoxelPerceptionTransformer', num_cams=6, embed_dims=C, decoder_on_bev=False,
+            encoder=encoder_cfg(C, 2 * C, num_layers=1), decoder=decoder_cfg(C, L)),
+        bbox_coder=dict(type='NMSFreeCoder', pc_range=PC, max_num=50, num_classes=17),
+        positional_encoding=dict(type='VoxelLearnedPositionalEncoding', num_feats=C // 2,
+                                 row_num_embed=grid[1], col_num_embed=grid[2], z_num_embed=grid[0]),
+        loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+        loss_bbox=dict(type='L1Loss', loss_weight=0.25), loss_iou=dict(type='GIoULoss', loss_weight=0.0),
+        loss_occupancy=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)).eval()
+    randomize(head, seed + 1)
+    Nq = grid[0] * grid[1] * grid[2]
+    g = torch.Generator().manual_seed(seed + 2)
+    bev_embed = torch.randn(Nq, 1, C, generator=g)
+    hs = torch.randn(L, nq, 1, C, generator=g)
+    init_ref = torch.rand(1, nq, 3, generator=g)
+    inter_refs = torch.rand(L, 1, nq, 3, generator=g)
+    inter_refs[0, 0, 0] = torch.tensor([0.0, 1.0, 0.5])       # clamped by inverse_sigmoid's eps
+
+    class _Stub(torch.nn.Module):
+        def __init__(self, decoder):
+            super().__init__()
+            self.decoder = decoder
+
+        def forward(self, *a, **k):
+            return bev_embed, hs, init_ref, inter_refs
+    all_keys = sorted(head.state_dict().keys())               # with the real transformer tree
+    head.transformer = _Stub(head.transformer.decoder)
+    with torch.no_grad():
+        outs = head(torch.zeros(6, 1, 196, C), [dict(sample_idx='scanA_vp0')])
+    sd = dict(head.state_dict())
+    cls2, box2 = ver_ref.detection_tail(sd, '', hs, init_ref, inter_refs, PC)
+    assert torch.allclose(outs['all_cls_scores'], cls2, atol=1e-6)
+    assert torch.allclose(outs['all_bbox_preds'], box2, atol=1e-6)
+    occ2 = ver_ref.occ_head(sd, '', bev_embed.permute(1, 0, 2), *grid, head.occ_xdim, head.occ_ydim, head.occ_zdim,
+                            occ_dims=16, refine_occ=False, only_occ=False)
+    assert torch.allclose(outs['occupancy_preds'], occ2, atol=1e-6)
+    keep = {k: v.numpy() for k, v in sd.items()
+            if k.startswith(('cls_branches', 'reg_branches', 'occ_', 'query_embedding'))}
+    out = {'bev_embed': bev_embed.numpy(), 'hs': hs.numpy(), 'init_ref': init_ref.numpy(),
+           'inter_refs': inter_refs.numpy(), 'grid': np.array(grid), 'all_cls_scores': outs['all_cls_scores'].numpy(),
+           'all_bbox_preds': outs['all_bbox_preds'].numpy(), 'occupancy_preds': outs['occupancy_preds'].numpy(),
+           'state_dict_keys': np.array(all_keys)}
+    out.update({f'sd.{k}': v for k, v in keep.items()})
+    np.savez_compressed(os.path.join(OUT, 'head_detection_c32.npz'), **out)
+    print('head detection ok')
+
+
 def main():
     assert mmcv_shim.reference_available(), 'needs /root/reference'
     os.makedirs(OUT, exist_ok=True)
@@ -354,6 +558,9 @@ def main():
     gen_encoder()
     gen_transformer()
     gen_head()
+    gen_msda3d()
+    gen_decoder()
+    gen_head_detection()
 
 
 if __name__ == '__main__':

@@ -290,6 +290,74 @@ class FFN(BaseModule):
         return identity + self.dropout_layer(out)
 
 
+@ATTENTION.register_module()
+class MultiheadAttention(BaseModule):
+    """mmcv 1.4.0 `mmcv.cnn.bricks.transformer.MultiheadAttention` restated (mmcv is not
+    vendored in the reference): a wrapper of nn.MultiheadAttention that adds the positional
+    encodings to query / key, applies proj_drop + dropout_layer and adds the identity.
+    vocc.py:141-145 builds it with embed_dims, num_heads=8, dropout=0.1 (deprecated kwarg:
+    becomes attn_drop and dropout_layer.drop_prob)."""
+
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0.,
+                 dropout_layer=dict(type='Dropout', drop_prob=0.), init_cfg=None,
+                 batch_first=False, **kwargs):
+        super().__init__(init_cfg)
+        dropout_layer = dict(dropout_layer) if dropout_layer else dropout_layer
+        if 'dropout' in kwargs:
+            attn_drop = kwargs['dropout']
+            dropout_layer['drop_prob'] = kwargs.pop('dropout')
+        self.embed_dims, self.num_heads, self.batch_first = embed_dims, num_heads, batch_first
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop, **kwargs)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.dropout_layer = build_dropout(dropout_layer) if dropout_layer else nn.Identity()
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None,
+                attn_mask=None, key_padding_mask=None, **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if identity is None:
+            identity = query
+        if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+            key_pos = query_pos
+        if query_pos is not None:
+            query = query + query_pos
+        if key_pos is not None:
+            key = key + key_pos
+        if self.batch_first:
+            query, key, value = query.transpose(0, 1), key.transpose(0, 1), value.transpose(0, 1)
+        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
+                        key_padding_mask=key_padding_mask)[0]
+        if self.batch_first:
+            out = out.transpose(0, 1)
+        return identity + self.dropout_layer(self.proj_drop(out))
+
+
+def register_detr_decoder_layer():
+    """mmcv's `DetrTransformerDecoderLayer` (vocc.py:139) = `BaseTransformerLayer` with the
+    6-op order check.  The reference owns a verbatim copy of BaseTransformerLayer
+    (M/custom_base_transformer_layer.py:37-260, `MyCustomBaseTransformerLayer`), so the shim class
+    subclasses THAT (reference-owned forward) with mmcv's batch_first=False default."""
+    if TRANSFORMER_LAYER.get('DetrTransformerDecoderLayer') is not None:
+        return TRANSFORMER_LAYER.get('DetrTransformerDecoderLayer')
+    base = import_reference('bevformer.modules.custom_base_transformer_layer').MyCustomBaseTransformerLayer
+
+    class DetrTransformerDecoderLayer(base):
+        def __init__(self, attn_cfgs, feedforward_channels, ffn_dropout=0.0, operation_order=None,
+                     act_cfg=dict(type='ReLU', inplace=True), norm_cfg=dict(type='LN'), ffn_num_fcs=2,
+                     **kwargs):
+            kwargs.setdefault('batch_first', False)
+            super().__init__(attn_cfgs=attn_cfgs, feedforward_channels=feedforward_channels,
+                             ffn_dropout=ffn_dropout, operation_order=operation_order, act_cfg=act_cfg,
+                             norm_cfg=norm_cfg, ffn_num_fcs=ffn_num_fcs, **kwargs)
+            assert len(operation_order) == 6
+            assert set(operation_order) == set(['self_attn', 'norm', 'cross_attn', 'ffn'])
+
+    TRANSFORMER_LAYER.register_module()(DetrTransformerDecoderLayer)
+    return DetrTransformerDecoderLayer
+
+
 class TransformerLayerSequence(BaseModule):
     def __init__(self, transformerlayers=None, num_layers=None, init_cfg=None):
         super().__init__(init_cfg)
@@ -506,6 +574,15 @@ def install():
             import h5py  # noqa: F401
         except ImportError:
             _mod('h5py')
+    # voxel_decoder.py:9-12 imports cv2 / matplotlib at module level and never uses them
+    for name in ('cv2', 'matplotlib'):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                _pkg(name)
+                if name == 'matplotlib':
+                    sys.modules['matplotlib'].pyplot = _mod('matplotlib.pyplot')
 
     # synthetic parents: __path__ points into the reference so its (broken)
     # package __init__ files are never executed

@@ -396,3 +396,233 @@ def get_occupancy_prediction(occupancy_preds, occupancy_classes=16, occ_threshol
     occ_class = p.argmax(dim=-1)
     occ_index, = torch.where(occ_class < occupancy_classes)
     return torch.stack([occ_index, occ_class[occ_index]], dim=-1)
+
+
+# =========================================================================== N2 / N3
+def voxel_multi_scale_deformable_attn_pytorch(value, value_spatial_shapes, sampling_locations,
+                                              attention_weights):
+    """The reference-owned 3-D sampler, M/voxel_temporal_self_attention.py:275-335, restated
+    (pinned to the unmodified function in tests/test_oracle_pins_reference.py).
+
+    value (bs, num_keys, num_heads, Dh); value_spatial_shapes (num_levels, 3) = (d, h, w);
+    sampling_locations (bs, nq, num_heads, num_levels, num_points, 3) = (x, y, z) in [0, 1];
+    attention_weights (bs, nq, num_heads, num_levels, num_points) -> (bs, nq, num_heads*Dh).
+    The reference's bare `.squeeze()` (:319) is `.squeeze(2)` here: identical unless some other
+    dimension has size 1, where the reference mis-shapes."""
+    bs, _, num_heads, embed_dims = value.shape
+    _, num_queries, _, num_levels, num_points, _ = sampling_locations.shape
+    shapes = [(int(d), int(h), int(w)) for d, h, w in value_spatial_shapes]
+    value_list = value.split([d * h * w for d, h, w in shapes], dim=1)
+    sampling_grids = 2 * sampling_locations - 1
+    sampled = []
+    for level, (d, h, w) in enumerate(shapes):
+        value_l = value_list[level].flatten(2).transpose(1, 2).reshape(bs * num_heads, embed_dims, d, h, w)
+        grid_l = sampling_grids[:, :, :, level].transpose(1, 2).flatten(0, 1).unsqueeze(1)
+        sampled.append(F.grid_sample(value_l, grid_l, mode='bilinear', padding_mode='zeros',
+                                     align_corners=False).squeeze(2))      # (bs*nh, Dh, nq, np)
+    attention_weights = attention_weights.transpose(1, 2).reshape(
+        bs * num_heads, 1, num_queries, num_levels * num_points)
+    out = (torch.stack(sampled, dim=-2).flatten(-2) * attention_weights).sum(-1)
+    return out.view(bs, num_heads * embed_dims, num_queries).transpose(1, 2).contiguous()
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    """M/voxel_decoder.py:35-50."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def voxel_custom_msda_forward(sd, pre, query, value, reference_points, spatial_shapes, identity=None,
+                              query_pos=None, num_heads=8, num_levels=1, num_points=4):
+    """VoxelCustomMSDeformableAttention.forward, M/voxel_decoder.py:236-322, batch_first=False, eval.
+    query (nq, bs, C); value (num_value, bs, C); reference_points (bs, nq, num_levels, 3);
+    spatial_shapes (num_levels, 3) = (d, h, w) -> (nq, bs, C)."""
+    if identity is None:
+        identity = query
+    if query_pos is not None:
+        query = query + query_pos
+    query, value = query.permute(1, 0, 2), value.permute(1, 0, 2)
+    bs, num_query, _ = query.shape
+    _, num_value, _ = value.shape
+    assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1] * spatial_shapes[:, 2]).sum()) == num_value
+    value = F.linear(value, sd[pre + 'value_proj.weight'], sd[pre + 'value_proj.bias'])
+    value = value.view(bs, num_value, num_heads, -1)
+    offsets = F.linear(query, sd[pre + 'sampling_offsets.weight'], sd[pre + 'sampling_offsets.bias']).view(
+        bs, num_query, num_heads, num_levels, num_points, 3)
+    weights = F.linear(query, sd[pre + 'attention_weights.weight'], sd[pre + 'attention_weights.bias']).view(
+        bs, num_query, num_heads, num_levels * num_points).softmax(-1).view(
+        bs, num_query, num_heads, num_levels, num_points)
+    if reference_points.shape[-1] != 3:
+        raise ValueError(f'Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.')
+    normalizer = torch.stack([spatial_shapes[..., 2], spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+    locations = reference_points[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
+    out = voxel_multi_scale_deformable_attn_pytorch(value, spatial_shapes, locations, weights)
+    out = F.linear(out, sd[pre + 'output_proj.weight'], sd[pre + 'output_proj.bias'])
+    return out.permute(1, 0, 2) + identity
+
+
+def multihead_self_attention_forward(sd, pre, query, query_pos, num_heads=8):
+    """mmcv 1.4.0 MultiheadAttention as the 'self_attn' op of DetrTransformerDecoderLayer
+    (vocc.py:141-145; called with key = value = query, key_pos = query_pos at
+    M/custom_base_transformer_layer.py:223-234), eval mode.  query (nq, bs, C)."""
+    nq, bs, C = query.shape
+    qk = query if query_pos is None else query + query_pos
+    Wq, Wk, Wv = sd[pre + 'attn.in_proj_weight'].chunk(3, 0)
+    bq, bk, bv = sd[pre + 'attn.in_proj_bias'].chunk(3, 0)
+    dh = C // num_heads
+
+    def heads(x, W, b):                       # (nq, bs, C) -> (bs, nh, nq, dh)
+        return F.linear(x, W, b).view(nq, bs, num_heads, dh).permute(1, 2, 0, 3)
+    q, k, v = heads(qk, Wq, bq), heads(qk, Wk, bk), heads(query, Wv, bv)
+    att = (q @ k.transpose(-1, -2) / dh ** 0.5).softmax(-1)
+    out = (att @ v).permute(2, 0, 1, 3).reshape(nq, bs, C)
+    out = F.linear(out, sd[pre + 'attn.out_proj.weight'], sd[pre + 'attn.out_proj.bias'])
+    return query + out
+
+
+def decoder_layer_forward(sd, pre, query, value, query_pos, reference_points, spatial_shapes,
+                          operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'), **kw):
+    """DetrTransformerDecoderLayer.forward = mmcv BaseTransformerLayer.forward (the reference's
+    copy: M/custom_base_transformer_layer.py:165-260), pre_norm=False, batch_first=False."""
+    C = query.shape[-1]
+    norm_index = attn_index = ffn_index = 0
+    for op in operation_order:
+        if op == 'self_attn':
+            query = multihead_self_attention_forward(sd, f'{pre}attentions.{attn_index}.', query, query_pos,
+                                                     num_heads=kw.get('num_heads', 8))
+            attn_index += 1
+        elif op == 'cross_attn':
+            query = voxel_custom_msda_forward(sd, f'{pre}attentions.{attn_index}.', query, value,
+                                              reference_points, spatial_shapes, query_pos=query_pos, **kw)
+            attn_index += 1
+        elif op == 'norm':
+            query = F.layer_norm(query, (C,), sd[f'{pre}norms.{norm_index}.weight'],
+                                 sd[f'{pre}norms.{norm_index}.bias'], 1e-5)
+            norm_index += 1
+        elif op == 'ffn':
+            query = ffn_forward(sd, f'{pre}ffns.{ffn_index}.', query)
+            ffn_index += 1
+    return query
+
+
+def decoder_forward(sd, pre, query, value, query_pos, reference_points, spatial_shapes, num_layers=6,
+                    reg_branches=None, return_intermediate=True, **kw):
+    """VoxelDetectionTransformerDecoder.forward, M/voxel_decoder.py:68-132.
+    query / query_pos (nq, bs, C); value (num_value, bs, C); reference_points (bs, nq, 3) in (0,1);
+    reg_branches: None or a list of callables (bs, nq, C) -> (bs, nq, >=5)."""
+    output = query
+    inter, inter_ref = [], []
+    for lid in range(num_layers):
+        output = decoder_layer_forward(sd, f'{pre}layers.{lid}.', output, value, query_pos,
+                                       reference_points[..., :3].unsqueeze(2), spatial_shapes, **kw)
+        output = output.permute(1, 0, 2)
+        if reg_branches is not None:
+            tmp = reg_branches[lid](output)
+            assert reference_points.shape[-1] == 3
+            new_ref = torch.zeros_like(reference_points)
+            new_ref[..., :2] = tmp[..., :2] + inverse_sigmoid(reference_points[..., :2])
+            new_ref[..., 2:3] = tmp[..., 4:5] + inverse_sigmoid(reference_points[..., 2:3])
+            reference_points = new_ref.sigmoid().detach()
+        output = output.permute(1, 0, 2)
+        if return_intermediate:
+            inter.append(output)
+            inter_ref.append(reference_points)
+    if return_intermediate:
+        return torch.stack(inter), torch.stack(inter_ref)
+    return output, reference_points
+
+
+def transformer_decode(sd, pre, voxel_embed, object_query_embed, bev_z, bev_h, bev_w, num_layers=6,
+                       reg_branches=None, **kw):
+    """The decoder half of VoxelPerceptionTransformer.forward, M/voxel_transformer.py:246-301
+    (decoder_on_bev=False).  voxel_embed (bs, Nq, C) from get_voxel_features;
+    object_query_embed (num_query, 2C) -> (voxel_embed (Nq, bs, C), inter_states, init_reference,
+    inter_references)."""
+    bs, _, C = voxel_embed.shape
+    query_pos, query = torch.split(object_query_embed, C, dim=1)
+    query_pos = query_pos.unsqueeze(0).expand(bs, -1, -1)
+    query = query.unsqueeze(0).expand(bs, -1, -1)
+    reference_points = F.linear(query_pos, sd[pre + 'reference_points.weight'],
+                                sd[pre + 'reference_points.bias']).sigmoid()
+    init_reference_out = reference_points
+    query, query_pos = query.permute(1, 0, 2), query_pos.permute(1, 0, 2)
+    voxel_embed = voxel_embed.permute(1, 0, 2)
+    inter_states, inter_references = decoder_forward(
+        sd, pre + 'decoder.', query, voxel_embed, query_pos, reference_points,
+        torch.tensor([[bev_z, bev_h, bev_w]]), num_layers=num_layers, reg_branches=reg_branches, **kw)
+    return voxel_embed, inter_states, init_reference_out, inter_references
+
+
+def temporal_self_attention_forward(sd, pre, query, reference_points, spatial_shapes, query_pos=None,
+                                    num_heads=8, num_levels=1, num_points=4, num_bev_queue=2):
+    """VoxelTemporalSelfAttention.forward, M/voxel_temporal_self_attention.py:129-273, with
+    value=None (no history: the current volume is stacked twice, :180-182), batch_first=True, eval.
+    query (bs, Nq, C); reference_points (bs*2, Nq, num_levels, 3) -> (bs, Nq, C).
+    NOTE the shipped module cannot run as initialised: init_weights assigns a 2-component bias of
+    num_heads*num_levels*num_bev_queue*num_points*2 elements (:113-124) to a Linear with
+    ...*3 outputs (:99-100); the arithmetic below is what forward computes once
+    sampling_offsets.bias has the Linear's own size."""
+    bs, len_bev, C = query.shape
+    value = torch.stack([query, query], 1).reshape(bs * 2, len_bev, C)
+    identity = query
+    if query_pos is not None:
+        query = query + query_pos
+    bs, num_query, embed_dims = query.shape
+    _, num_value, _ = value.shape
+    assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1] * spatial_shapes[:, 2]).sum()) == num_value
+    assert num_bev_queue == 2
+    query = torch.cat([value[:bs], query], -1)
+    value = F.linear(value, sd[pre + 'value_proj.weight'], sd[pre + 'value_proj.bias'])
+    value = value.reshape(bs * num_bev_queue, num_value, num_heads, -1)
+    offsets = F.linear(query, sd[pre + 'sampling_offsets.weight'], sd[pre + 'sampling_offsets.bias']).view(
+        bs, num_query, num_heads, num_bev_queue, num_levels, num_points, 3)
+    weights = F.linear(query, sd[pre + 'attention_weights.weight'], sd[pre + 'attention_weights.bias']).view(
+        bs, num_query, num_heads, num_bev_queue, num_levels * num_points).softmax(-1).view(
+        bs, num_query, num_heads, num_bev_queue, num_levels, num_points)
+    weights = weights.permute(0, 3, 1, 2, 4, 5).reshape(
+        bs * num_bev_queue, num_query, num_heads, num_levels, num_points).contiguous()
+    offsets = offsets.permute(0, 3, 1, 2, 4, 5, 6).reshape(
+        bs * num_bev_queue, num_query, num_heads, num_levels, num_points, 3)
+    if reference_points.shape[-1] != 3:
+        raise ValueError(f'Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.')
+    normalizer = torch.stack([spatial_shapes[..., 2], spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+    locations = reference_points[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
+    out = voxel_multi_scale_deformable_attn_pytorch(value, spatial_shapes, locations, weights)
+    out = out.permute(1, 2, 0).view(num_query, embed_dims, bs, num_bev_queue).mean(-1).permute(2, 0, 1)
+    out = F.linear(out, sd[pre + 'output_proj.weight'], sd[pre + 'output_proj.bias'])
+    return out + identity
+
+
+def detection_tail(sd, pre, hs, init_reference, inter_references, pc_range, num_reg_fcs=2):
+    """The per-decoder-layer classification / box outputs of VoxelFormerOccupancyHead.forward,
+    HEAD:583-611 (default branch; identical code at :385-412 for only_det).  hs (num_dec, nq, bs, C);
+    init_reference (bs, nq, 3); inter_references (num_dec, bs, nq, 3).
+    cls_branches[l] = [Linear, LayerNorm, ReLU] x num_reg_fcs + Linear; reg_branches[l] = [Linear, ReLU] x
+    num_reg_fcs + Linear (HEAD:181-197)."""
+    hs = hs.permute(0, 2, 1, 3)
+    C = hs.shape[-1]
+    outputs_classes, outputs_coords = [], []
+    for lvl in range(hs.shape[0]):
+        reference = inverse_sigmoid(init_reference if lvl == 0 else inter_references[lvl - 1])
+        x = hs[lvl]
+        for i in range(num_reg_fcs):
+            x = F.linear(x, sd[f'{pre}cls_branches.{lvl}.{3 * i}.weight'], sd[f'{pre}cls_branches.{lvl}.{3 * i}.bias'])
+            x = F.relu(F.layer_norm(x, (C,), sd[f'{pre}cls_branches.{lvl}.{3 * i + 1}.weight'],
+                                    sd[f'{pre}cls_branches.{lvl}.{3 * i + 1}.bias'], 1e-5))
+        k = 3 * num_reg_fcs
+        outputs_classes.append(F.linear(x, sd[f'{pre}cls_branches.{lvl}.{k}.weight'], sd[f'{pre}cls_branches.{lvl}.{k}.bias']))
+        tmp = hs[lvl]
+        for i in range(num_reg_fcs):
+            tmp = F.relu(F.linear(tmp, sd[f'{pre}reg_branches.{lvl}.{2 * i}.weight'], sd[f'{pre}reg_branches.{lvl}.{2 * i}.bias']))
+        k = 2 * num_reg_fcs
+        tmp = F.linear(tmp, sd[f'{pre}reg_branches.{lvl}.{k}.weight'], sd[f'{pre}reg_branches.{lvl}.{k}.bias']).clone()
+        assert reference.shape[-1] == 3
+        tmp[..., 0:2] += reference[..., 0:2]
+        tmp[..., 0:2] = tmp[..., 0:2].sigmoid()
+        tmp[..., 4:5] += reference[..., 2:3]
+        tmp[..., 4:5] = tmp[..., 4:5].sigmoid()
+        tmp[..., 0:1] = tmp[..., 0:1] * (pc_range[3] - pc_range[0]) + pc_range[0]
+        tmp[..., 1:2] = tmp[..., 1:2] * (pc_range[4] - pc_range[1]) + pc_range[1]
+        tmp[..., 4:5] = tmp[..., 4:5] * (pc_range[5] - pc_range[2]) + pc_range[2]
+        outputs_coords.append(tmp)
+    return torch.stack(outputs_classes), torch.stack(outputs_coords)

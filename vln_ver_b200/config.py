@@ -8,14 +8,15 @@ POINT_CLOUD_RANGE = [-6.0, -6.0, -1.5, 6.0, 6.0, 2.0]      # vocc.py:9
 
 def vocc_head_cfg(bev_z=4, bev_h=15, bev_w=15, num_cams=6, embed_dims=768, only_occ=False,
                   refine_occ=True, occupancy_size=(0.1, 0.1, 0.1), occ_dims=128, num_layers=3,
-                  pc_range=POINT_CLOUD_RANGE, with_decoder=None, ffn_dims=None):
+                  pc_range=POINT_CLOUD_RANGE, with_decoder=None, ffn_dims=None, num_decoder_layers=6,
+                  num_query=100):
     """Defaults reproduce vocc.py (15x15x4, refine_occ=True, full decoder tree).  For the
     per-voxel head of the grid sweeps use `occupancy_size=per_voxel_occupancy_size(...)`,
     `refine_occ=False`, `only_occ=True`."""
     _dim_ = embed_dims
     with_decoder = (not only_occ) if with_decoder is None else with_decoder
     decoder = dict(
-        type='VoxelDetectionTransformerDecoder', num_layers=6, return_intermediate=True,
+        type='VoxelDetectionTransformerDecoder', num_layers=num_decoder_layers, return_intermediate=True,
         transformerlayers=dict(
             type='DetrTransformerDecoderLayer',
             attn_cfgs=[dict(type='MultiheadAttention', embed_dims=_dim_, num_heads=8, dropout=0.1),
@@ -26,7 +27,7 @@ def vocc_head_cfg(bev_z=4, bev_h=15, bev_w=15, num_cams=6, embed_dims=768, only_
             operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))
     cfg = dict(
         type='VoxelFormerOccupancyHead', bev_h=bev_h, bev_w=bev_w, bev_z=bev_z, getbev=None,
-        num_query=100, num_classes=17, in_channels=_dim_, sync_cls_avg_factor=True,
+        num_query=num_query, num_classes=17, in_channels=_dim_, sync_cls_avg_factor=True,
         with_box_refine=True, as_two_stage=False, point_cloud_range=list(pc_range),
         occupancy_size=list(occupancy_size), occ_dims=occ_dims, occupancy_classes=16,
         only_occ=only_occ, only_det=False, refine_occ=refine_occ,
@@ -60,6 +61,8 @@ def vocc_head_cfg(bev_z=4, bev_h=15, bev_w=15, num_cams=6, embed_dims=768, only_
         cfg['transformer']['encoder']['transformerlayers']['ffn_cfgs'] = dict(
             type='FFN', embed_dims=_dim_, feedforward_channels=1024, num_fcs=2, ffn_drop=0.,
             act_cfg=dict(type='ReLU', inplace=True))
+        if with_decoder:
+            decoder['transformerlayers']['ffn_cfgs']['embed_dims'] = _dim_      # vocc.py:148 hard-codes 768 too
     return copy.deepcopy(cfg)
 
 

@@ -7,5 +7,8 @@ from .precision import set_compute_dtype                                        
 from .spatial_cross_attention import MSDeformableAttention3D, SpatialCrossAttention   # noqa: F401
 from .voxel_encoder import VoxelFormerEncoder, VoxelFormerLayer                       # noqa: F401
 from .voxel_positional_embedding import VoxelLearnedPositionalEncoding                # noqa: F401
-from .voxel_transformer import VoxelDetectionTransformerDecoder, VoxelPerceptionTransformer  # noqa: F401
+from .voxel_decoder import (BaseTransformerLayer, DetrTransformerDecoderLayer, MultiheadAttention,  # noqa: F401
+                            VoxelCustomMSDeformableAttention, VoxelDetectionTransformerDecoder)
+from .voxel_temporal_self_attention import VoxelTemporalSelfAttention                  # noqa: F401
+from .voxel_transformer import VoxelPerceptionTransformer                             # noqa: F401
 from .voxelformer_occupancy_head import FocalLoss, VoxelFormerOccupancyHead           # noqa: F401

@@ -1,5 +1,6 @@
 """VoxelPerceptionTransformer -- mirror of
-projects/mmdet3d_plugin/bevformer/modules/voxel_transformer.py (:24-301), encoder side.
+projects/mmdet3d_plugin/bevformer/modules/voxel_transformer.py (:24-301): get_voxel_features
+(encoder side, the hot path) and forward (encoder + detection decoder).
 
 get_voxel_features (A8): the per-view tokens get cams_embeds + level_embeds added and are
 re-laid out (Ncam, B, S, C) -> (B*Ncam, S, C) by ONE kernel (ver_feat_embed) instead of the
@@ -12,10 +13,10 @@ from torch.autograd.function import Function, once_differentiable
 from torch.nn.init import normal_
 
 from .. import ops
-from ..registry import (TRANSFORMER, TRANSFORMER_LAYER_SEQUENCE, BaseModule,
-                        build_transformer_layer_sequence, xavier_init)
+from ..registry import TRANSFORMER, BaseModule, build_transformer_layer_sequence, xavier_init
 from .precision import PrecisionMixin
 from .spatial_cross_attention import MSDeformableAttention3D
+from .voxel_decoder import VoxelDetectionTransformerDecoder  # noqa: F401  (registered there; re-exported)
 
 
 class _FeatEmbed(Function):
@@ -34,23 +35,6 @@ class _FeatEmbed(Function):
         g_cams = g.sum((0, 2)) if ctx.has_cams and ctx.needs_input_grad[1] else None
         g_level = g.sum((0, 1, 2)) if ctx.needs_input_grad[2] else None
         return g_feats, g_cams, g_level, None
-
-
-@TRANSFORMER_LAYER_SEQUENCE.register_module()
-class VoxelDetectionTransformerDecoder(BaseModule):
-    """Placeholder so that vocc.py's `decoder=dict(type='VoxelDetectionTransformerDecoder', ...)`
-    builds.  The detection decoder is outside this round's scope (SURVEY.md section 8(f) row N2);
-    calling it raises."""
-
-    def __init__(self, *args, num_layers=6, return_intermediate=False, transformerlayers=None, **kwargs):
-        super().__init__(kwargs.get('init_cfg'))
-        self.num_layers = num_layers
-        self.return_intermediate = return_intermediate
-        self.transformerlayers_cfg = transformerlayers
-
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError('VoxelDetectionTransformerDecoder (3-D box decoder) is not part of '
-                                  'the lift+encode hot path; build the head with only_occ=True')
 
 
 @TRANSFORMER.register_module()
@@ -124,4 +108,22 @@ class VoxelPerceptionTransformer(PrecisionMixin, BaseModule):
                                               prev_bev=prev_bev, **kwargs)
         if self.decoder is None:
             return voxel_embed.permute(1, 0, 2), None, None, None
-        raise NotImplementedError('detection decoder: SURVEY.md section 8(f) N2 (next)')
+        if self.decoder_on_bev:
+            raise NotImplementedError('decoder_on_bev=True (voxel2bev MLP / pool, reference :262-285) is not on '
+                                      'the vocc.py path (vocc.py:113 sets decoder_on_bev=False)')
+        # decoder half (reference :246-301): object queries -> reference points -> 6 decoder layers
+        # reading the encoded voxel volume through the 3-D deformable sampler
+        bs = mlvl_feats.shape[1]
+        query_pos, query = torch.split(object_query_embed, self.embed_dims, dim=1)
+        query_pos = query_pos.unsqueeze(0).expand(bs, -1, -1)
+        query = query.unsqueeze(0).expand(bs, -1, -1)
+        reference_points = self.reference_points(query_pos).sigmoid()
+        init_reference_out = reference_points
+        query = query.permute(1, 0, 2)
+        query_pos = query_pos.permute(1, 0, 2)
+        voxel_embed = voxel_embed.permute(1, 0, 2)
+        inter_states, inter_references = self.decoder(
+            query=query, key=None, value=voxel_embed, query_pos=query_pos, reference_points=reference_points,
+            reg_branches=reg_branches, cls_branches=cls_branches, spatial_shapes=[[bev_z, bev_h, bev_w]],
+            level_start_index=[0], **kwargs)
+        return voxel_embed, inter_states, init_reference_out, inter_references

@@ -2,8 +2,10 @@
 projects/mmdet3d_plugin/bevformer/dense_heads/voxelformer_occupancy_head.py (HEAD):
 query embedding -> VoxelPerceptionTransformer -> [up_sample] -> occ_proj -> occ_branches
 (HEAD:300-308, :323-352, :551-580), sigmoid focal occupancy loss (HEAD:1386-1444) and the
-sparse decode (HEAD:1505-1524).  The DETR-style box / layout branches are a different task
-("OUT OF SCOPE") and are not built.
+sparse decode (HEAD:1505-1524).  With a decoder in the transformer cfg (vocc.py default,
+only_occ=False) the DETR-style forward tail is built too: query embeddings,
+cls / reg / layout branches and the box decoding of HEAD:368-625.  The detection LOSSES
+(Hungarian assignment, L1 / GIoU) are a different task and are not built.
 """
 import copy
 
@@ -14,6 +16,7 @@ from .. import ops
 from ..registry import (HAVE_MMCV, HEADS, LOSSES, BaseModule, bias_init_with_prob,
                         build_loss, build_positional_encoding, build_transformer)
 from .precision import PrecisionMixin
+from .voxel_decoder import inverse_sigmoid
 from .voxel_encoder import apply_layernorm
 
 
@@ -79,6 +82,11 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         self.getbev = getbev
         self.with_box_refine, self.as_two_stage = with_box_refine, as_two_stage
         self.num_classes, self.in_channels, self.num_query = num_classes, in_channels, num_query
+        self.num_reg_fcs, self.num_layout_query = num_reg_fcs, num_layout_query
+        self.code_size = kwargs.get('code_size', 10)                          # HEAD:111-114
+        self.layout_range = [-50.0, -50.0, -5.0, 50.0, 50.0, 5.0]             # HEAD:91
+        # mmdet DETRHead: sigmoid classification has no background column
+        self.cls_out_channels = num_classes if (loss_cls or {}).get('use_sigmoid', False) else num_classes + 1
         self.occ_weights = occ_weights
         self.pc_range = (bbox_coder or {}).get('pc_range', point_cloud_range)
         self.real_w = self.pc_range[3] - self.pc_range[0]
@@ -103,10 +111,34 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         assert positional_encoding['num_feats'] * 2 == self.embed_dims
         self.loss_occupancy = build_loss(loss_occupancy)
         self.loss_cls = build_loss(loss_cls) if (loss_cls and not only_occ) else None
+        # frozen nn.Parameter in the reference too (HEAD:115-123, :161-162): part of its state_dict
+        self.code_weights = nn.Parameter(torch.tensor(
+            list(code_weights) if code_weights is not None else [1.0] * 8 + [0.0, 0.0]), requires_grad=False)
         self._init_layers()
 
     def _init_layers(self):
-        """voxel_embedding, occ_proj, occ_branches, up_sample (HEAD:226-258)."""
+        """detection branches when a decoder exists (HEAD:179-231), then voxel_embedding, occ_proj,
+        occ_branches, up_sample (HEAD:226-258)."""
+        if self.transformer.decoder is not None:
+            C = self.embed_dims
+
+            def mlp(out, norm):
+                layers = []
+                for _ in range(self.num_reg_fcs):
+                    layers += [nn.Linear(C, C)] + ([nn.LayerNorm(C), nn.ReLU(inplace=True)] if norm else [nn.ReLU()])
+                return nn.Sequential(*layers, nn.Linear(C, out))
+            num_pred = self.transformer.decoder.num_layers + (1 if self.as_two_stage else 0)
+
+            def clones(m):
+                if self.with_box_refine:
+                    return nn.ModuleList([copy.deepcopy(m) for _ in range(num_pred)])
+                return nn.ModuleList([m for _ in range(num_pred)])
+            self.cls_branches = clones(mlp(self.cls_out_channels, True))
+            self.reg_branches = clones(mlp(self.code_size, False))
+            self.layout_branches = clones(mlp(self.code_size, False))
+            if not self.as_two_stage:
+                self.query_embedding = nn.Embedding(self.num_query, C * 2)
+                self.query_layout_embedding = nn.Embedding(self.num_layout_query, C * 2)
         self.voxel_embedding = nn.Embedding(self.bev_num, self.embed_dims)
         if self.bev_z == self.occ_zdim:
             self.occ_proj = nn.Linear(self.embed_dims, self.occ_dims)
@@ -127,6 +159,9 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
     def init_weights(self):
         self.transformer.init_weights()
         self.positional_encoding.init_weights()
+        if self.loss_cls is not None and self.loss_cls.use_sigmoid and hasattr(self, 'cls_branches'):
+            for m in self.cls_branches:                                        # HEAD:272-276
+                nn.init.constant_(m[-1].bias, bias_init_with_prob(0.01))
         if self.loss_occupancy.use_sigmoid:
             nn.init.constant_(self.occ_branches[-1].bias, bias_init_with_prob(0.01))
 
@@ -176,17 +211,49 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         if needs_pos:       # A9: only a self-attention layer ever reads it
             voxel_pos = self.positional_encoding(
                 torch.zeros((bs, self.bev_z, self.bev_h, self.bev_w), device=voxel_queries.device))
-        bev_embed = self.transformer.get_voxel_features(
-            mlvl_feats, voxel_queries, self.bev_z, self.bev_h, self.bev_w,
-            grid_length=(self.real_h / self.bev_h, self.real_w / self.bev_w), bev_pos=voxel_pos,
-            img_metas=img_metas, prev_bev=prev_bev, **cam)
-        if only_bev:
-            return bev_embed
-        outs = {'bev_embed': bev_embed if self.only_occ else bev_embed.permute(1, 0, 2),
-                'all_cls_scores': None, 'all_bbox_preds': None, 'all_layout_preds': None,
-                'occupancy_preds': self._occupancy_tail(bev_embed, bs), 'flow_preds': None,
-                'enc_cls_scores': None, 'enc_bbox_preds': None, 'enc_occupancy_preds': None}
-        return outs
+        feat_args = dict(grid_length=(self.real_h / self.bev_h, self.real_w / self.bev_w), bev_pos=voxel_pos,
+                         img_metas=img_metas, prev_bev=prev_bev, **cam)
+        if only_bev or self.only_occ or self.transformer.decoder is None:
+            bev_embed = self.transformer.get_voxel_features(
+                mlvl_feats, voxel_queries, self.bev_z, self.bev_h, self.bev_w, **feat_args)
+            if only_bev:
+                return bev_embed
+            return {'bev_embed': bev_embed if self.only_occ else bev_embed.permute(1, 0, 2),
+                    'all_cls_scores': None, 'all_bbox_preds': None, 'all_layout_preds': None,
+                    'occupancy_preds': self._occupancy_tail(bev_embed, bs), 'flow_preds': None,
+                    'enc_cls_scores': None, 'enc_bbox_preds': None, 'enc_occupancy_preds': None}
+        # lift + encode + decode (HEAD:368-625; only_det :370-430, add_layout :431-535, default :537-625)
+        bev_embed, hs, init_reference, inter_references = self.transformer(
+            mlvl_feats, voxel_queries, self.query_embedding.weight, self.bev_z, self.bev_h, self.bev_w,
+            reg_branches=self.reg_branches if self.with_box_refine else None,
+            cls_branches=self.cls_branches if self.as_two_stage else None, **feat_args)
+        cls, boxes, layouts = self._detection_tail(hs, init_reference, inter_references)
+        return {'bev_embed': bev_embed, 'all_cls_scores': cls, 'all_bbox_preds': boxes,
+                'all_layout_preds': layouts if self.add_layout else None,
+                'occupancy_preds': None if self.only_det else self._occupancy_tail(bev_embed.permute(1, 0, 2), bs),
+                'flow_preds': None, 'enc_cls_scores': None, 'enc_bbox_preds': None, 'enc_occupancy_preds': None}
+
+    def _detection_tail(self, hs, init_reference, inter_references):
+        """hs (num_dec, num_query, bs, C) -> class scores (num_dec, bs, num_query, cls_out) and boxes
+        (num_dec, bs, num_query, code_size) with centre x, y (slots 0, 1) and z (slot 4) offset from the
+        layer's input reference point, squashed and mapped into pc_range (HEAD:590-611); layout boxes
+        likewise into layout_range (HEAD:497-511)."""
+        hs = hs.permute(0, 2, 1, 3).float()
+        classes, coords, layouts = [], [], []
+
+        def place(t, reference, rng):
+            xy = (t[..., 0:2] + reference[..., 0:2]).sigmoid()
+            z = (t[..., 4:5] + reference[..., 2:3]).sigmoid()
+            return torch.cat([xy[..., 0:1] * (rng[3] - rng[0]) + rng[0], xy[..., 1:2] * (rng[4] - rng[1]) + rng[1],
+                              t[..., 2:4], z * (rng[5] - rng[2]) + rng[2], t[..., 5:]], -1)
+        for lvl in range(hs.shape[0]):
+            reference = inverse_sigmoid(init_reference if lvl == 0 else inter_references[lvl - 1])
+            assert reference.shape[-1] == 3
+            classes.append(self.cls_branches[lvl](hs[lvl]))
+            coords.append(place(self.reg_branches[lvl](hs[lvl]), reference, self.pc_range))
+            if self.add_layout:
+                layouts.append(place(self.layout_branches[lvl](hs[lvl]), reference, self.layout_range))
+        return torch.stack(classes), torch.stack(coords), (torch.stack(layouts) if layouts else None)
 
     # ------------------------------------------------------------------ A11
     def loss_only_occupancy(self, gt_bboxes_list, gt_labels_list, point_coords, occ_gts, flow_gts,

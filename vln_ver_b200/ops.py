@@ -172,6 +172,82 @@ MultiScaleDeformableAttnFunction_fp32 = MultiScaleDeformableAttnFunction
 MultiScaleDeformableAttnFunction_fp16 = MultiScaleDeformableAttnFunction
 
 
+# ------------------------------------------------------------------ N2 / N3: 3-D (voxel volume) sampler
+def _shapes3_arg(spatial_shapes):
+    if isinstance(spatial_shapes, torch.Tensor):
+        spatial_shapes = spatial_shapes.tolist()
+    flat = [int(v) for dhw in spatial_shapes for v in dhw]
+    if len(flat) % 3:
+        raise VerError('3-D spatial_shapes must be (num_levels, 3) = (d, h, w)')
+    return (c_int32 * len(flat))(*flat), len(flat) // 3
+
+
+def voxel_ms_deform_attn_forward(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """sm_100a replacement of voxel_multi_scale_deformable_attn_pytorch
+    (M/voxel_temporal_self_attention.py:275-335; same argument order and meaning).
+    value (Bv, S, NH, Dh) fp32|fp16, S = sum d*h*w; sampling_locations (Bv, Nq, NH, NL, NP, 3) = (x, y, z);
+    attention_weights (Bv, Nq, NH, NL, NP) -> (Bv, Nq, NH*Dh)."""
+    _need_cuda(value, sampling_locations, attention_weights)
+    value = _c(value)
+    loc = _c(sampling_locations, torch.float32)
+    w = _c(attention_weights, torch.float32)
+    Bv, S, NH, Dh = value.shape
+    _, Nq, _, NL, NP, last = loc.shape
+    if last != 3:
+        raise VerError(f'sampling_locations last dim must be 3 (x, y, z), got {last}')
+    assert loc.shape[0] == Bv and loc.shape[2] == NH and w.shape == loc.shape[:-1]
+    shapes, nl = _shapes3_arg(value_spatial_shapes)
+    assert nl == NL, (nl, NL)
+    out = torch.empty((Bv, Nq, NH * Dh), dtype=value.dtype, device=value.device)
+    check(lib.ver_msda3d_forward(_code(value.dtype), _ptr(value), shapes, NL, _ptr(loc), _ptr(w), _ptr(out),
+                                 Bv, S, NH, Dh, Nq, NP, _stream()))
+    return out
+
+
+def voxel_ms_deform_attn_backward(value, value_spatial_shapes, sampling_locations, attention_weights,
+                                  grad_output):
+    """Gradients of voxel_ms_deform_attn_forward: (grad_value, grad_loc, grad_w), all fp32."""
+    _need_cuda(value, sampling_locations, attention_weights, grad_output)
+    value = _c(value)
+    loc = _c(sampling_locations, torch.float32)
+    w = _c(attention_weights, torch.float32)
+    go = _c(grad_output, value.dtype)
+    Bv, S, NH, Dh = value.shape
+    _, Nq, _, NL, NP, _ = loc.shape
+    shapes, _ = _shapes3_arg(value_spatial_shapes)
+    gv = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+    gl = torch.empty(loc.shape, dtype=torch.float32, device=value.device)
+    gw = torch.empty(w.shape, dtype=torch.float32, device=value.device)
+    check(lib.ver_msda3d_backward(_code(value.dtype), _ptr(value), shapes, NL, _ptr(loc), _ptr(w), _ptr(go),
+                                  _ptr(gv), _ptr(gl), _ptr(gw), Bv, S, NH, Dh, Nq, NP, _stream()))
+    return gv, gl, gw
+
+
+class VoxelMultiScaleDeformableAttnFunction(Function):
+    """Autograd node of the 3-D sampler (the reference differentiates through F.grid_sample)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, sampling_locations, attention_weights):
+        ctx.shapes = value_spatial_shapes.tolist() if isinstance(value_spatial_shapes, torch.Tensor) \
+            else [list(x) for x in value_spatial_shapes]
+        out = voxel_ms_deform_attn_forward(value, ctx.shapes, sampling_locations, attention_weights)
+        ctx.save_for_backward(value, sampling_locations, attention_weights)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, loc, w = ctx.saved_tensors
+        gv, gl, gw = voxel_ms_deform_attn_backward(value, ctx.shapes, loc, w, grad_output.contiguous())
+        return gv.to(value.dtype), None, gl.to(loc.dtype), gw.to(w.dtype)
+
+
+def voxel_multi_scale_deformable_attn(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """Differentiable call with the reference function's signature."""
+    return VoxelMultiScaleDeformableAttnFunction.apply(value, value_spatial_shapes, sampling_locations,
+                                                       attention_weights)
+
+
 # ------------------------------------------------------------------ fused SCA sampler
 class Visibility:
     """Per-forward camera geometry products shared by the three encoder layers."""
