@@ -645,3 +645,23 @@ def test_full_size_properties():
         assert torch.equal(t1, t1b)
         assert rel_err(t2, 2 * t1.float()) < 1e-3
         assert (t1[count == 0] == 0).all()
+
+
+def test_device_prefetcher_copies_each_batch_once_in_order():
+    """vln_ver_b200.ingest.DevicePrefetcher: one batch ahead on a copy stream, values intact, nothing copied
+    beyond the last batch."""
+    from vln_ver_b200.ingest import DevicePrefetcher, pin
+    g = torch.Generator().manual_seed(0)
+    host = [pin(dict(feats=torch.randn(3, 2, 196, 64, generator=g), l2i=torch.randn(2, 3, 4, 4, generator=g)))
+            for _ in range(5)]
+    assert all(t.is_pinned() for b in host for t in b.values())
+    pf = DevicePrefetcher(iter(host), 'cuda')
+    seen = 0
+    for i, db in enumerate(pf):
+        y = db['feats'] * 2.0                       # consume on the compute stream
+        assert db['feats'].is_cuda and torch.equal(db['feats'].cpu(), host[i]['feats'])
+        assert torch.equal(db['l2i'].cpu(), host[i]['l2i']) and torch.equal(y.cpu(), host[i]['feats'] * 2.0)
+        seen += 1
+    assert seen == 5
+    assert pf.h2d_bytes == sum(t.numel() * t.element_size() for b in host for t in b.values())
+    assert list(DevicePrefetcher(iter([]), 'cuda')) == []
