@@ -202,10 +202,30 @@ def test_refine_occ_default_branch_tail_vs_oracle():
     with torch.no_grad():
         ref = ver_ref.occ_head(sd, '', bev, *grid, 24, 24, 7, occ_dims=16, refine_occ=True, only_occ=False)
     head = head.to(DEV).eval()
-    with torch.no_grad():
-        y = head._occupancy_tail(cuda(bev), 2)
-    assert y.shape == (2, 7 * 24 * 24, 16)
-    assert rel_err(y, ref) < 1e-4       # three chained 768x768x75-tap library convolutions in fp32
+    for lattice in (True, False):       # lattice form (vln_ver_b200/upsample.py, the default) and the stack as written
+        head.lattice_up_sample = lattice
+        with torch.no_grad():
+            y = head._occupancy_tail(cuda(bev), 2)
+        assert y.shape == (2, 7 * 24 * 24, 16)
+        assert rel_err(y, ref) < 1e-4       # three chained 768x768x75-tap library convolutions in fp32
+    # gradients of the lattice form against the dense stack (same library, different factorisation)
+    grads = {}
+    for lattice in (True, False):
+        head.lattice_up_sample = lattice
+        head.zero_grad()
+        x = cuda(bev).requires_grad_(True)
+        head._occupancy_tail(x, 2).square().sum().backward()
+        grads[lattice] = [x.grad] + [p.grad.clone() for p in head.up_sample.parameters()]
+    for a, b in zip(grads[True], grads[False]):
+        assert rel_err(a, b) < 1e-4
+    # fp16 storage: lattice vs dense
+    V.set_compute_dtype(head, torch.float16)
+    outs = {}
+    for lattice in (True, False):
+        head.lattice_up_sample = lattice
+        with torch.no_grad():
+            outs[lattice] = head._occupancy_tail(cuda(bev), 2)
+    assert rel_err(outs[True], outs[False]) < 5e-3
 
 
 # ------------------------------------------------------------------ full lift+encode vs oracle

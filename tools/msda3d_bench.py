@@ -19,8 +19,13 @@ def bench(name, Bv, grid, Nq, NH=8, Dh=96, NP=4, dtype=torch.float16, iters=10):
     dev = 'cuda'
     g = torch.Generator(device=dev).manual_seed(0)
     v = torch.randn(Bv, S, NH, Dh, device=dev, generator=g).to(dtype)
-    # queries near their own voxel (self-attn) or anywhere (decoder): offsets of a few voxels
-    base = torch.rand(Bv, Nq, 1, 1, 1, 3, device=dev, generator=g)
+    # reference points: the query's own voxel centre when every voxel is a query (self-attention, the
+    # reference's ref_2d grid, M/voxel_encoder.py:47-76), anywhere in the volume for the box queries
+    if Nq == S:
+        zs, ys, xs = torch.meshgrid(*[(torch.arange(n, device=dev) + 0.5) / n for n in grid], indexing='ij')
+        base = torch.stack((xs, ys, zs), -1).view(1, S, 1, 1, 1, 3).expand(Bv, -1, -1, -1, -1, -1)
+    else:
+        base = torch.rand(Bv, Nq, 1, 1, 1, 3, device=dev, generator=g)
     loc = (base + (torch.rand(Bv, Nq, NH, 1, NP, 3, device=dev, generator=g) - 0.5) * 0.2).contiguous()
     w = torch.rand(Bv, Nq, NH, 1, NP, device=dev, generator=g).softmax(-1)
     go = torch.randn(Bv, Nq, NH * Dh, device=dev, generator=g).to(dtype)
