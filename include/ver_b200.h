@@ -125,6 +125,20 @@ int ver_msda3d_backward(int dtype, const void* value, const int32_t* shapes_dhw,
                         float* grad_w, int Bv, int S, int NH, int Dh, int Nq, int NP,
                         ver_stream_t stream);
 
+/* ---------------------------------------------------------------- N1: up_sample stack
+ * The three ConvTranspose3d(768, 768, (3,5,5), stride (1,2,2), padding (2,4,4), dilation (2,2,2),
+ * output_padding (0,1,1)) of HEAD:254-258 (applied at HEAD:557-560) in lattice form: a layer is a library
+ * GEMM  cols[b, i, k, :] = e_in[b, i, :] @ W[:, k, :]  (k = (kz*5 + ky)*5 + kx, 75 taps) followed by
+ *   e_out[b, (oz,oy,ox), :] = sum of cols[b, (iz,iy,ix), k, :] over the taps with
+ *   oz = iz - 2 + 2 kz,  oy = s iy - 2 + ky,  ox = s ix - 2 + kx      (s = 1 first layer, 2 after)
+ * which is ver_convt_col2im (gather form, no atomics).  ver_convt_im2col is its adjoint (backward).
+ *   cols / grad_cols  [B, Z*Hi*Wi, 75, C] dtype        out / grad_out  [B, Z*(s Hi)*(s Wi), C] dtype
+ * C must be a multiple of 8 (fp16) / 4 (fp32); buffers 16-byte aligned. */
+int ver_convt_col2im(int dtype, const void* cols, void* out, int B, int Z, int Hi, int Wi, int s, int C,
+                     ver_stream_t stream);
+int ver_convt_im2col(int dtype, const void* grad_out, void* grad_cols, int B, int Z, int Hi, int Wi, int s, int C,
+                     ver_stream_t stream);
+
 /* ---------------------------------------------------------------- A3 (+) A4 (+) A5 fused
  * The sampling part of SpatialCrossAttention.forward (M/spatial_cross_attention.py:138-173)
  * with MSDeformableAttention3D's softmax / location arithmetic (:340-374) fused in, for

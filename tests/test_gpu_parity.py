@@ -202,30 +202,70 @@ def test_refine_occ_default_branch_tail_vs_oracle():
     with torch.no_grad():
         ref = ver_ref.occ_head(sd, '', bev, *grid, 24, 24, 7, occ_dims=16, refine_occ=True, only_occ=False)
     head = head.to(DEV).eval()
-    for lattice in (True, False):       # lattice form (vln_ver_b200/upsample.py, the default) and the stack as written
-        head.lattice_up_sample = lattice
+    modes = ('auto', 'gemm', 'lattice', 'dense')   # lattice form (GEMM + col2im kernel | cuDNN) and the stack as written
+    for mode in modes:
+        head.up_sample_mode = mode
         with torch.no_grad():
             y = head._occupancy_tail(cuda(bev), 2)
         assert y.shape == (2, 7 * 24 * 24, 16)
         assert rel_err(y, ref) < 1e-4       # three chained 768x768x75-tap library convolutions in fp32
     # gradients of the lattice form against the dense stack (same library, different factorisation)
     grads = {}
-    for lattice in (True, False):
-        head.lattice_up_sample = lattice
+    for mode in modes[1:]:
+        head.up_sample_mode = mode
         head.zero_grad()
         x = cuda(bev).requires_grad_(True)
+        n0 = V.launch_count()
         head._occupancy_tail(x, 2).square().sum().backward()
-        grads[lattice] = [x.grad] + [p.grad.clone() for p in head.up_sample.parameters()]
-    for a, b in zip(grads[True], grads[False]):
-        assert rel_err(a, b) < 1e-4
+        if mode == 'gemm':
+            assert V.launch_count() - n0 >= 6, 'three col2im + three im2col launches'
+        grads[mode] = [x.grad] + [p.grad.clone() for p in head.up_sample.parameters()]
+    for mode in ('gemm', 'lattice'):
+        for a, b in zip(grads[mode], grads['dense']):
+            assert rel_err(a, b) < 1e-4
     # fp16 storage: lattice vs dense
     V.set_compute_dtype(head, torch.float16)
     outs = {}
-    for lattice in (True, False):
-        head.lattice_up_sample = lattice
+    for mode in modes[1:]:
+        head.up_sample_mode = mode
         with torch.no_grad():
-            outs[lattice] = head._occupancy_tail(cuda(bev), 2)
-    assert rel_err(outs[True], outs[False]) < 5e-3
+            outs[mode] = head._occupancy_tail(cuda(bev), 2)
+    assert rel_err(outs['gemm'], outs['dense']) < 5e-3 and rel_err(outs['lattice'], outs['dense']) < 5e-3
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('s', [1, 2])
+def test_convt_col2im_kernels(dtype, s):
+    """ver_convt_col2im against the library lattice convolution it replaces (identity weights make the GEMM a
+    copy, so the transposed convolution of e with W = delta IS col2im of tiled e), and ver_convt_im2col as its
+    exact adjoint: <col2im(X), G> == <X, im2col(G)> on random data at the vocc.py layer-3 size."""
+    import torch.nn.functional as F
+    B, Z, Hi, Wi, C = 2, 3, 5, 4, 16
+    g = torch.Generator().manual_seed(s)
+    cols = torch.randn(B, Z * Hi * Wi, 75, C, generator=g).to(dtype)
+    out = ops.convt_col2im(cuda(cols), Z, Hi, Wi, s)
+    # restatement: every tap k of every input position is its own input channel of a transposed convolution
+    # whose weight routes channel (k, c) through tap k only
+    w = torch.zeros(75 * C, C, 3, 5, 5, dtype=torch.float64)
+    for kz in range(3):
+        for ky in range(5):
+            for kx in range(5):
+                k = (kz * 5 + ky) * 5 + kx
+                w[k * C:(k + 1) * C, :, kz, ky, kx] = torch.eye(C, dtype=torch.float64)
+    xin = cols.double().view(B, Z, Hi, Wi, 75 * C).permute(0, 4, 1, 2, 3)
+    ref = F.conv_transpose3d(xin, w, None, stride=(1, s, s), padding=(2, 2, 2), output_padding=(0, s - 1, s - 1),
+                             dilation=(2, 1, 1))
+    ref = ref.flatten(2).transpose(1, 2)
+    assert rel_err(out, ref) < TOL[dtype]
+    # adjoint at full size: C = 768, 4 x 60 x 60 -> 4 x 120 x 120
+    Z, Hi, Wi, C = 4, 60 // s, 60 // s, 768
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    X = torch.randn(1, Z * Hi * Wi, 75, C, device=DEV, generator=gen).to(dtype)
+    G = torch.randn(1, Z * s * Hi * s * Wi, C, device=DEV, generator=gen).to(dtype)
+    lhs = (ops.convt_col2im(X, Z, Hi, Wi, s).double() * G.double()).sum().item()
+    rhs = (X.double() * ops.convt_im2col(G, Z, Hi, Wi, s).double()).sum().item()
+    scale = X.double().norm().item() * G.double().norm().item()
+    assert abs(lhs - rhs) < (1e-6 if dtype == torch.float32 else 2e-3) * scale
 
 
 # ------------------------------------------------------------------ full lift+encode vs oracle

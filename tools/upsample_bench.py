@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vln_ver_b200.upsample import up_sample_lattice  # noqa: E402
+from vln_ver_b200.upsample import up_sample_gemm, up_sample_lattice  # noqa: E402
 
 
 def timeit(f, iters=5, warm=2):
@@ -49,15 +49,21 @@ def main():
 
             def lattice(inp=x):
                 return up_sample_lattice(inp, convs, dtype=dtype)
+
+            def gemm(inp=x):
+                return up_sample_gemm(inp, convs, dtype=dtype)
             with torch.no_grad():
-                ref, y = dense(), lattice()
+                ref, y, yg = dense(), lattice(), gemm()
                 err = ((ref.float() - y.float()).abs().max() / ref.float().abs().max()).item()
-                t_d, t_l = timeit(dense), timeit(lattice)
+                errg = ((ref.float() - yg.float()).abs().max() / ref.float().abs().max()).item()
+                t_d, t_l, t_g = timeit(dense), timeit(lattice), timeit(gemm)
             flop_d, flop_l = 1.672e12 * bs, 0.478e12 * bs
             print(json.dumps({'dtype': str(dtype).split('.')[-1], 'batch': bs, 'pass': 'forward',
-                              'dense_ms': round(t_d, 3), 'lattice_ms': round(t_l, 3), 'speedup': round(t_d / t_l, 2),
-                              'dense_TFLOPs': round(flop_d / t_d / 1e9, 1), 'lattice_TFLOPs': round(flop_l / t_l / 1e9, 1),
-                              'max_rel_diff': err}), flush=True)
+                              'dense_ms': round(t_d, 3), 'lattice_cudnn_ms': round(t_l, 3), 'lattice_gemm_ms': round(t_g, 3),
+                              'speedup_gemm_vs_dense': round(t_d / t_g, 2),
+                              'dense_TFLOPs': round(flop_d / t_d / 1e9, 1), 'lattice_cudnn_TFLOPs': round(flop_l / t_l / 1e9, 1),
+                              'lattice_gemm_TFLOPs': round(flop_l / t_g / 1e9, 1),
+                              'max_rel_diff_cudnn': err, 'max_rel_diff_gemm': errg}), flush=True)
             if bs == 1:
                 xg = x.clone().requires_grad_(True)
 
@@ -67,6 +73,7 @@ def main():
                             p.grad = None
                         xg.grad = None
                         y = up_sample_lattice(xg, convs, dtype=dtype) if fn == 'lattice' else \
+                            up_sample_gemm(xg, convs, dtype=dtype) if fn == 'gemm' else \
                             nn.Sequential(*convs)(xg) if dtype == torch.float32 else None
                         if y is None:       # fp16 dense with autograd through the casts
                             y = xg
@@ -77,9 +84,11 @@ def main():
                         y.float().square().mean().backward()
                     return run
                 t_d, t_l = timeit(fb('dense'), iters=3, warm=1), timeit(fb('lattice'), iters=3, warm=1)
+                t_g = timeit(fb('gemm'), iters=3, warm=1)
                 print(json.dumps({'dtype': str(dtype).split('.')[-1], 'batch': bs, 'pass': 'forward+backward',
-                                  'dense_ms': round(t_d, 3), 'lattice_ms': round(t_l, 3),
-                                  'speedup': round(t_d / t_l, 2)}), flush=True)
+                                  'dense_ms': round(t_d, 3), 'lattice_cudnn_ms': round(t_l, 3),
+                                  'lattice_gemm_ms': round(t_g, 3), 'speedup_gemm_vs_dense': round(t_d / t_g, 2)}),
+                      flush=True)
 
 
 if __name__ == '__main__':

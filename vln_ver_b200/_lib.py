@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libver_b200.so')
 
 VER_F32, VER_F16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class VerError(RuntimeError):
@@ -46,6 +46,8 @@ def _load():
                                        c_int, c_int, c_int, c_int, P]),
         'ver_msda3d_backward': (c_int, [c_int, P, ctypes.POINTER(c_int32), c_int, P, P, P, P, P, P, c_int,
                                         c_int, c_int, c_int, c_int, c_int, P]),
+        'ver_convt_col2im': (c_int, [c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+        'ver_convt_im2col': (c_int, [c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
         'ver_sca_forward': (c_int, [c_int, P, c_int, P, c_int, P, P, P] + [c_int] * 10 + [P]),
         'ver_sca_backward': (c_int, [c_int, P, c_int, P, c_int, P, P, P, P, P, P, P] + [c_int] * 10 + [P]),
         'ver_visibility_order_workspace': (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),

@@ -15,7 +15,7 @@ import torch.nn as nn
 from .. import ops
 from ..registry import (HAVE_MMCV, HEADS, LOSSES, BaseModule, bias_init_with_prob,
                         build_loss, build_positional_encoding, build_transformer)
-from ..upsample import lattice_supported, up_sample_lattice
+from ..upsample import lattice_supported, up_sample, up_sample_gemm, up_sample_lattice
 from .precision import PrecisionMixin
 from .voxel_decoder import inverse_sigmoid
 from .voxel_encoder import apply_layernorm
@@ -80,7 +80,9 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         self.only_occ, self.only_det, self.add_layout = only_occ, only_det, add_layout
         self.occ_loss_type, self.occ_head_type = occ_loss_type, occ_head_type
         self.refine_occ = refine_occ
-        self.lattice_up_sample = True     # False: the three ConvTranspose3d as written (A/B switch for tests)
+        # 'auto': lattice form (GEMM + col2im kernel on CUDA); 'gemm' / 'lattice': force one execution of it;
+        # 'dense': the three ConvTranspose3d as written (A/B switch for tests and tools/upsample_bench.py)
+        self.up_sample_mode = 'auto'
         self.getbev = getbev
         self.with_box_refine, self.as_two_stage = with_box_refine, as_two_stage
         self.num_classes, self.in_channels, self.num_query = num_classes, in_channels, num_query
@@ -177,10 +179,12 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         if self.refine_occ and not self.only_occ:
             x = x.view(bs, C, self.bev_z, self.bev_h, self.bev_w)
             w_dtype = cd
-            if self.lattice_up_sample and lattice_supported(self.up_sample):
+            mode = self.up_sample_mode if lattice_supported(self.up_sample) else 'dense'
+            if mode != 'dense':
                 # same values with 3.5x fewer FLOPs: the data of every layer lives on the even-even
                 # lattice of its output, the rest is the bare bias (vln_ver_b200/upsample.py)
-                x = up_sample_lattice(x, self.up_sample, dtype=w_dtype)
+                fn = {'auto': up_sample, 'gemm': up_sample_gemm, 'lattice': up_sample_lattice}[mode]
+                x = fn(x, self.up_sample, dtype=w_dtype)
             else:
                 for conv in self.up_sample:
                     x = nn.functional.conv_transpose3d(

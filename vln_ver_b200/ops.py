@@ -248,6 +248,45 @@ def voxel_multi_scale_deformable_attn(value, value_spatial_shapes, sampling_loca
                                                        attention_weights)
 
 
+# ------------------------------------------------------------------ N1: col2im of the lattice-form up_sample
+def convt_col2im(cols, Z, Hi, Wi, s):
+    """cols (B, Z*Hi*Wi, 75, C) -> (B, Z*(s Hi)*(s Wi), C): ver_convt_col2im (HEAD:254-258 in lattice form)."""
+    _need_cuda(cols)
+    cols = _c(cols)
+    B, n_in, taps, C = cols.shape
+    assert taps == 75 and n_in == Z * Hi * Wi, (cols.shape, Z, Hi, Wi)
+    out = torch.empty((B, Z * s * Hi * s * Wi, C), dtype=cols.dtype, device=cols.device)
+    check(lib.ver_convt_col2im(_code(cols.dtype), _ptr(cols), _ptr(out), B, Z, Hi, Wi, s, C, _stream()))
+    return out
+
+
+def convt_im2col(grad_out, Z, Hi, Wi, s):
+    """adjoint of convt_col2im: grad_out (B, Z*(s Hi)*(s Wi), C) -> (B, Z*Hi*Wi, 75, C)."""
+    _need_cuda(grad_out)
+    grad_out = _c(grad_out)
+    B, n_out, C = grad_out.shape
+    assert n_out == Z * s * Hi * s * Wi
+    gcols = torch.empty((B, Z * Hi * Wi, 75, C), dtype=grad_out.dtype, device=grad_out.device)
+    check(lib.ver_convt_im2col(_code(grad_out.dtype), _ptr(grad_out), _ptr(gcols), B, Z, Hi, Wi, s, C, _stream()))
+    return gcols
+
+
+class ConvTCol2ImFunction(Function):
+    @staticmethod
+    def forward(ctx, cols, Z, Hi, Wi, s):
+        ctx.dims = (Z, Hi, Wi, s)
+        return convt_col2im(cols, Z, Hi, Wi, s)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        return convt_im2col(grad_out.contiguous(), *ctx.dims), None, None, None, None
+
+
+def convt_col2im_fn(cols, Z, Hi, Wi, s):
+    return ConvTCol2ImFunction.apply(cols, Z, Hi, Wi, s)
+
+
 # ------------------------------------------------------------------ fused SCA sampler
 class Visibility:
     """Per-forward camera geometry products shared by the three encoder layers."""

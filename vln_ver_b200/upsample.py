@@ -16,7 +16,16 @@ convolution of a ones field: boundary-exact, negligible cost).  The data-carryin
 (H W + H W + 4 H W) Z x 75 taps x 768^2 MACs = 0.478 TFLOP at 15x15x4 instead of 1.672: 3.5x fewer FLOPs, the
 same values up to fp32 summation order (tests: fp64 equality on CPU, fp32 on the GPU against the oracle).
 The dense (bs, C, Z, 8H, 8W) tensor HEAD:564 reinterprets is materialised once at the end.
-The convolutions themselves are library calls (cuDNN), like the GEMMs of the encoder.
+
+Two executions of the lattice form:
+  * `up_sample_lattice`  -- the small transposed convolutions as library calls (cuDNN); runs anywhere torch does,
+    used by the CPU tests to pin the algebra in fp64;
+  * `up_sample_gemm`     -- channels-last, each layer = one library GEMM  cols = e @ W  (M = lattice positions,
+    K = 768, N = 75 * 768) + the hand-written gather `ver_convt_col2im` (csrc/col2im.cu); its backward is the
+    adjoint kernel `ver_convt_im2col` + the GEMM's own autograd.  Measured on B200 (profiles/r01w, r01x): cuDNN
+    runs the stack AS WRITTEN at 0.95-1.1 PFLOP/s in fp16, but the small lattice convolutions only at 0.11-0.41;
+    the GEMM form keeps the 3.5x FLOP saving at GEMM speed.
+`up_sample` picks: CUDA -> GEMM form; otherwise the cuDNN/CPU lattice form.
 """
 import torch
 import torch.nn.functional as F
@@ -66,3 +75,47 @@ def up_sample_lattice(x, convs, dtype=None):
     out = prev_bias.to(dtype).view(1, C, 1, 1, 1).expand(bs, C, Z, 2 * H, 2 * W).contiguous()
     out[:, :, :, 0::2, 0::2] += e
     return out
+
+
+def _bias_field_response(conv, prev_bias, Z, H, W, acc, device):
+    """convT(constant field prev_bias) sampled on the output lattice -> (Z*H*W, Cout), boundary exact."""
+    u = torch.einsum('iokhw,i->okhw', conv.weight.to(acc), prev_bias.to(acc)).unsqueeze(0)
+    ones = torch.ones((1, 1, Z, H, W), dtype=acc, device=device)
+    c = F.conv_transpose3d(ones, u, None, stride=1, padding=(2, 2, 2), dilation=(2, 1, 1))      # (1, Cout, Z, H, W)
+    return c.flatten(2).transpose(1, 2)[0]
+
+
+def up_sample_gemm(x, convs, dtype=None, col2im=None):
+    """Same contract as up_sample_lattice; GEMM + col2im execution (CUDA).  `col2im(cols, Z, Hi, Wi, s)` defaults to
+    the libver_b200 kernel; tests inject a torch restatement to check the algebra on CPU."""
+    if col2im is None:
+        from . import ops
+        col2im = ops.convt_col2im_fn
+    dtype = dtype or x.dtype
+    acc = torch.float64 if dtype == torch.float64 else torch.float32
+    bs, C, Z, H, W = x.shape
+    e = x.to(dtype).flatten(2).transpose(1, 2).contiguous()                  # (bs, Z*H*W, C) channels-last
+    prev_bias = None
+    for layer, conv in enumerate(convs):
+        _check(conv)
+        cin, cout = conv.weight.shape[:2]
+        # (Cin, Cout, 3, 5, 5) -> (Cin, 75 * Cout), column = tap * Cout + channel
+        wmat = conv.weight.to(dtype).permute(0, 2, 3, 4, 1).reshape(cin, 75 * cout)
+        cols = (e.reshape(-1, cin) @ wmat).view(bs, Z * H * W, 75, cout)
+        s = 1 if layer == 0 else 2
+        e = col2im(cols, Z, H, W, s)                                          # (bs, Z*(sH)*(sW), Cout)
+        H, W = s * H, s * W
+        if layer > 0:
+            e = e + _bias_field_response(conv, prev_bias, Z, H, W, acc, e.device).to(dtype)
+        prev_bias = conv.bias if conv.bias is not None else conv.weight.new_zeros(cout)
+    C = e.shape[-1]
+    out = prev_bias.to(dtype).view(1, C, 1, 1, 1).expand(bs, C, Z, 2 * H, 2 * W).contiguous()
+    out[:, :, :, 0::2, 0::2] += e.view(bs, Z, H, W, C).permute(0, 4, 1, 2, 3)
+    return out
+
+
+def up_sample(x, convs, dtype=None):
+    """HEAD:557-560 `self.up_sample(bev_for_occ)`: the GEMM form on CUDA, the library lattice form elsewhere."""
+    if x.is_cuda:
+        return up_sample_gemm(x, convs, dtype)
+    return up_sample_lattice(x, convs, dtype)
