@@ -85,6 +85,24 @@ def _bias_field_response(conv, prev_bias, Z, H, W, acc, device):
     return c.flatten(2).transpose(1, 2)[0]
 
 
+_WMAT_CACHE = {}
+
+
+def _weight_matrix(weight, dtype):
+    """(Cin, Cout, 3, 5, 5) -> (Cin, 75 * Cout), column = tap * Cout + channel, in `dtype`.  Under no_grad
+    (inference) the 88 MB fp16 matrix is cached per parameter version, like fused_layer.half_of."""
+    cin, cout = weight.shape[:2]
+    if torch.is_grad_enabled() and weight.requires_grad:
+        return weight.to(dtype).permute(0, 2, 3, 4, 1).reshape(cin, 75 * cout)
+    key = (id(weight), dtype)
+    hit = _WMAT_CACHE.get(key)
+    tag = (weight._version, weight.data_ptr(), weight.device)
+    if hit is None or hit[0] != tag:
+        hit = (tag, weight.detach().to(dtype).permute(0, 2, 3, 4, 1).reshape(cin, 75 * cout).contiguous())
+        _WMAT_CACHE[key] = hit
+    return hit[1]
+
+
 def up_sample_gemm(x, convs, dtype=None, col2im=None):
     """Same contract as up_sample_lattice; GEMM + col2im execution (CUDA).  `col2im(cols, Z, Hi, Wi, s)` defaults to
     the libver_b200 kernel; tests inject a torch restatement to check the algebra on CPU."""
@@ -99,8 +117,7 @@ def up_sample_gemm(x, convs, dtype=None, col2im=None):
     for layer, conv in enumerate(convs):
         _check(conv)
         cin, cout = conv.weight.shape[:2]
-        # (Cin, Cout, 3, 5, 5) -> (Cin, 75 * Cout), column = tap * Cout + channel
-        wmat = conv.weight.to(dtype).permute(0, 2, 3, 4, 1).reshape(cin, 75 * cout)
+        wmat = _weight_matrix(conv.weight, dtype)
         cols = (e.reshape(-1, cin) @ wmat).view(bs, Z * H * W, 75, cout)
         s = 1 if layer == 0 else 2
         e = col2im(cols, Z, H, W, s)                                          # (bs, Z*(sH)*(sW), Cout)
