@@ -25,7 +25,7 @@ Two executions of the lattice form:
     adjoint kernel `ver_convt_im2col` + the GEMM's own autograd.  Measured on B200 (profiles/r01w, r01x): cuDNN
     runs the stack AS WRITTEN at 0.95-1.1 PFLOP/s in fp16, but the small lattice convolutions only at 0.11-0.41;
     the GEMM form keeps the 3.5x FLOP saving at GEMM speed.
-`up_sample` picks: CUDA -> GEMM form; otherwise the cuDNN/CPU lattice form.
+`up_sample` picks per dtype / batch from those measurements (see its docstring).
 """
 import torch
 import torch.nn.functional as F
@@ -132,7 +132,21 @@ def up_sample_gemm(x, convs, dtype=None, col2im=None):
 
 
 def up_sample(x, convs, dtype=None):
-    """HEAD:557-560 `self.up_sample(bev_for_occ)`: the GEMM form on CUDA, the library lattice form elsewhere."""
-    if x.is_cuda:
-        return up_sample_gemm(x, convs, dtype)
-    return up_sample_lattice(x, convs, dtype)
+    """HEAD:557-560 `self.up_sample(bev_for_occ)`.  Picks the execution from the measurements in
+    profiles/r01x_upsample_bench.txt: fp32 -> GEMM + col2im lattice form (4-6x faster forward, 18x faster
+    forward+backward than the stack as written); fp16 -> cuDNN runs the stack as written at ~1 PFLOP/s, which the
+    lattice form only beats from ~8 panoramas of 4x15x15 on (9.2 vs 12.2 ms at 8), so small batches stay dense.
+    Off CUDA: the library lattice form."""
+    dtype = dtype or x.dtype
+    if not x.is_cuda:
+        return up_sample_lattice(x, convs, dtype)
+    positions = x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4]
+    if dtype == torch.float16 and positions < 8 * 900:
+        y = x.to(dtype)
+        for conv in convs:
+            _check(conv)
+            y = F.conv_transpose3d(y, conv.weight.to(dtype), None if conv.bias is None else conv.bias.to(dtype),
+                                   stride=conv.stride, padding=conv.padding, output_padding=conv.output_padding,
+                                   dilation=conv.dilation)
+        return y
+    return up_sample_gemm(x, convs, dtype)
