@@ -131,22 +131,32 @@ def up_sample_gemm(x, convs, dtype=None, col2im=None):
     return out
 
 
-def up_sample(x, convs, dtype=None):
-    """HEAD:557-560 `self.up_sample(bev_for_occ)`.  Picks the execution from the measurements in
-    profiles/r01x_upsample_bench.txt: fp32 -> GEMM + col2im lattice form (4-6x faster forward, 18x faster
-    forward+backward than the stack as written); fp16 -> cuDNN runs the stack as written at ~1 PFLOP/s, which the
-    lattice form only beats from ~8 panoramas of 4x15x15 on (9.2 vs 12.2 ms at 8), so small batches stay dense.
-    Off CUDA: the library lattice form."""
+def up_sample_dense(x, convs, dtype=None):
+    """The stack exactly as the reference writes it (three library ConvTranspose3d calls) in `dtype`."""
     dtype = dtype or x.dtype
-    if not x.is_cuda:
-        return up_sample_lattice(x, convs, dtype)
-    positions = x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4]
+    y = x.to(dtype)
+    for conv in convs:
+        y = F.conv_transpose3d(y, conv.weight.to(dtype), None if conv.bias is None else conv.bias.to(dtype),
+                               stride=conv.stride, padding=conv.padding, output_padding=conv.output_padding,
+                               dilation=conv.dilation)
+    return y
+
+
+def pick_execution(dtype, positions, on_cuda):
+    """Which execution `up_sample` uses, from the measurements in profiles/r01x_upsample_bench.txt:
+    fp32 -> GEMM + col2im lattice form (4-6x faster forward, 18x faster forward+backward than the stack as
+    written); fp16 -> cuDNN runs the stack as written at ~1 PFLOP/s, which the lattice form only beats from
+    ~8 panoramas of 4x15x15 on (9.2 vs 12.2 ms at 8), so smaller inputs stay dense.  Off CUDA: the library
+    lattice form.  `positions` = batch * Z * H * W of the input volume."""
+    if not on_cuda:
+        return 'lattice'
     if dtype == torch.float16 and positions < 8 * 900:
-        y = x.to(dtype)
-        for conv in convs:
-            _check(conv)
-            y = F.conv_transpose3d(y, conv.weight.to(dtype), None if conv.bias is None else conv.bias.to(dtype),
-                                   stride=conv.stride, padding=conv.padding, output_padding=conv.output_padding,
-                                   dilation=conv.dilation)
-        return y
-    return up_sample_gemm(x, convs, dtype)
+        return 'dense'
+    return 'gemm'
+
+
+def up_sample(x, convs, dtype=None):
+    """HEAD:557-560 `self.up_sample(bev_for_occ)`."""
+    dtype = dtype or x.dtype
+    how = pick_execution(dtype, x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4], x.is_cuda)
+    return {'dense': up_sample_dense, 'gemm': up_sample_gemm, 'lattice': up_sample_lattice}[how](x, convs, dtype)
