@@ -52,3 +52,83 @@ class DevicePrefetcher:
             nxt = next(it, None)
             pending = self._start(nxt) if nxt is not None else None
             yield db
+
+
+# --------------------------------------------------------------------------- file formats either side of the path
+def view_keys(sample_idx, num_cams=6):
+    """HDF5 dataset names of one panorama's view features, `<scan>_<viewpoint>_i<elevation>_<heading>`
+    (voxelformer.py:317-318).  The shipped code reads elevation 1 x 6 headings (:287-288); its commented-out
+    loop (:284-286) is the 18-view order: elevation-major (0, 1, 2), then heading 0..5 -- the camera order of
+    `VoxelFormerEncoder._camera_tensors`."""
+    scan, vp = sample_idx.split('_')
+    if num_cams == 6:
+        elevations = (1,)
+    elif num_cams == 18:
+        elevations = (0, 1, 2)
+    else:
+        raise ValueError(f'{num_cams} views: the feature files hold 6 headings x 3 elevations')
+    return ['%s_%s_i%s_%s' % (scan, vp, e, deg) for e in elevations for deg in range(6)]
+
+
+def _open_h5(path, mode='r'):
+    try:
+        import h5py
+    except ImportError as e:       # the container format is h5py's; nothing here re-implements it
+        raise ImportError('reading / writing the reference\'s HDF5 feature files needs h5py '
+                          '(not installed in this environment); pass `opener=` to use another container') from e
+    return h5py.File(path, mode)
+
+
+class ViewFeatureStore:
+    """`VoxelFormer.get_image_feature` (voxelformer.py:317-325) for whole batches: datasets are (1, 197, C) ViT
+    tokens in fp16 or fp32; the CLS token is dropped and the rest cast to fp32 (`f[key][:, 1:, :].astype(np.float32)`);
+    every dataset is read once and kept (the reference's `_feature_store`).  `batch()` assembles the
+    (Ncam, B, 196, C) layout the head takes, in pinned memory, ready for `DevicePrefetcher`.
+    `opener(path)` must return a mapping `key -> array-like` usable as a context manager (default: h5py.File)."""
+
+    def __init__(self, opener=None, pinned=True):
+        self.opener = opener or _open_h5
+        self.pinned = pinned
+        self._feature_store = {}
+
+    def get(self, img_ft_file, key):
+        import numpy as np
+        ft = self._feature_store.get((img_ft_file, key))
+        if ft is None:
+            with self.opener(img_ft_file) as f:
+                ft = np.asarray(f[key])[:, 1:, :].astype(np.float32)          # (1, 196, C)
+            self._feature_store[(img_ft_file, key)] = ft
+        return ft
+
+    def panorama(self, img_ft_file, sample_idx, num_cams=6):
+        import numpy as np
+        return np.array([self.get(img_ft_file, k) for k in view_keys(sample_idx, num_cams)])    # (Ncam, 1, 196, C)
+
+    def batch(self, img_metas, num_cams=6):
+        """img_metas: dicts with `file_name` and `sample_idx` (voxelformer.py:282-288) -> (Ncam, B, 196, C) fp32."""
+        import numpy as np
+        feats = np.concatenate([self.panorama(m['file_name'], m['sample_idx'], num_cams) for m in img_metas], axis=1)
+        t = torch.from_numpy(np.ascontiguousarray(feats))
+        return t.pin_memory() if self.pinned and torch.cuda.is_available() else t
+
+
+def export_bev_embed(path, img_metas, bev_embed, embed_dims, bev_z, bev_h, bev_w, opener=None):
+    """The `getbev` export of VoxelFormerOccupancyHead.forward (HEAD:627-638): one gzip-compressed float64 dataset
+    of shape (C, Z, H, W) per panorama, keyed by `sample_idx`, appended to `path`.  `bev_embed` is the
+    (Nq, bs, C) tensor of the default branch; as in the reference the (Nq, C) block of a panorama is
+    REINTERPRETED as (C, Z, H, W) (`.view`, not a permute -- SURVEY.md A4.3).  The reference handles bs = 1 and
+    keys by img_metas[0]; a batch writes one dataset per panorama."""
+    import os
+    nq, bs, c = bev_embed.shape
+    assert c == embed_dims and nq == bev_z * bev_h * bev_w and len(img_metas) == bs
+    per_sample = bev_embed.detach().permute(1, 0, 2).contiguous().view(bs, embed_dims, bev_z, bev_h, bev_w)
+    data = per_sample.double().cpu().numpy()
+    opener = opener or _open_h5
+    outf = opener(path, 'a' if os.path.exists(path) else 'w')
+    try:
+        for b, meta in enumerate(img_metas):
+            key = meta['sample_idx']
+            outf.create_dataset(key, data[b].shape, dtype='float', compression='gzip')
+            outf[key][...] = data[b]
+    finally:
+        outf.close()

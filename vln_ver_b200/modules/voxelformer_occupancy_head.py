@@ -239,6 +239,9 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
             reg_branches=self.reg_branches if self.with_box_refine else None,
             cls_branches=self.cls_branches if self.as_two_stage else None, **feat_args)
         cls, boxes, layouts = self._detection_tail(hs, init_reference, inter_references)
+        if self.getbev is not None:                  # HEAD:627-638: append the voxel features to an HDF5 file
+            from ..ingest import export_bev_embed
+            export_bev_embed(self.getbev, img_metas, bev_embed, self.embed_dims, self.bev_z, self.bev_h, self.bev_w)
         return {'bev_embed': bev_embed, 'all_cls_scores': cls, 'all_bbox_preds': boxes,
                 'all_layout_preds': layouts if self.add_layout else None,
                 'occupancy_preds': None if self.only_det else self._occupancy_tail(bev_embed.permute(1, 0, 2), bs),
