@@ -176,7 +176,8 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         cd = self.compute_dtype or bev_embed.dtype
         C = self.embed_dims
         x = bev_embed.contiguous()
-        if self.refine_occ and not self.only_occ:
+        # the add_layout branch of the reference never up-samples (HEAD:459-470), the only_occ branch neither (:334)
+        if self.refine_occ and not self.only_occ and not self.add_layout:
             x = x.view(bs, C, self.bev_z, self.bev_h, self.bev_w)
             w_dtype = cd
             mode = self.up_sample_mode if lattice_supported(self.up_sample) else 'dense'
