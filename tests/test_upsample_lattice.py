@@ -117,12 +117,13 @@ def test_col2im_library_entry_points_validate_arguments():
 
 
 def test_dense_execution_and_the_choice_between_them():
+    import vln_ver_b200 as V
     from vln_ver_b200.upsample import pick_execution, up_sample, up_sample_dense
     convs = stack(6, seed=5)
     x = torch.randn(1, 6, 2, 3, 3, dtype=torch.float64)
     assert torch.equal(up_sample_dense(x, convs), convs(x))
-    assert (up_sample(x, convs) - convs(x)).abs().max().item() < 1e-13          # CPU -> library lattice form
-    assert pick_execution(torch.float64, 900, False) == 'lattice'
-    assert pick_execution(torch.float32, 900, True) == 'gemm'
-    assert pick_execution(torch.float16, 900, True) == 'dense'                   # one shipped-size panorama
-    assert pick_execution(torch.float16, 8 * 900, True) == 'gemm'
+    with pytest.raises(V.VerError):                        # the product dispatcher has no CPU path
+        up_sample(x, convs)
+    assert pick_execution(torch.float32, 900) == 'gemm'
+    assert pick_execution(torch.float16, 900) == 'dense'                   # one shipped-size panorama
+    assert pick_execution(torch.float16, 8 * 900) == 'gemm'

@@ -18,8 +18,8 @@ same values up to fp32 summation order (tests: fp64 equality on CPU, fp32 on the
 The dense (bs, C, Z, 8H, 8W) tensor HEAD:564 reinterprets is materialised once at the end.
 
 Two executions of the lattice form:
-  * `up_sample_lattice`  -- the small transposed convolutions as library calls (cuDNN); runs anywhere torch does,
-    used by the CPU tests to pin the algebra in fp64;
+  * `up_sample_lattice`  -- the small transposed convolutions as library calls; runs anywhere torch does: it is what
+    the CPU tests use to pin the algebra in fp64 (and an A/B arm of tools/upsample_bench.py), not a product path;
   * `up_sample_gemm`     -- channels-last, each layer = one library GEMM  cols = e @ W  (M = lattice positions,
     K = 768, N = 75 * 768) + the hand-written gather `ver_convt_col2im` (csrc/col2im.cu); its backward is the
     adjoint kernel `ver_convt_im2col` + the GEMM's own autograd.  Measured on B200 (profiles/r01w, r01x): cuDNN
@@ -142,21 +142,23 @@ def up_sample_dense(x, convs, dtype=None):
     return y
 
 
-def pick_execution(dtype, positions, on_cuda):
-    """Which execution `up_sample` uses, from the measurements in profiles/r01x_upsample_bench.txt:
+def pick_execution(dtype, positions):
+    """Which execution `up_sample` uses on the GPU, from the measurements in profiles/r01x_upsample_bench.txt:
     fp32 -> GEMM + col2im lattice form (4-6x faster forward, 18x faster forward+backward than the stack as
     written); fp16 -> cuDNN runs the stack as written at ~1 PFLOP/s, which the lattice form only beats from
-    ~8 panoramas of 4x15x15 on (9.2 vs 12.2 ms at 8), so smaller inputs stay dense.  Off CUDA: the library
-    lattice form.  `positions` = batch * Z * H * W of the input volume."""
-    if not on_cuda:
-        return 'lattice'
+    ~8 panoramas of 4x15x15 on (9.2 vs 12.2 ms at 8), so smaller inputs stay dense.
+    `positions` = batch * Z * H * W of the input volume."""
     if dtype == torch.float16 and positions < 8 * 900:
         return 'dense'
     return 'gemm'
 
 
 def up_sample(x, convs, dtype=None):
-    """HEAD:557-560 `self.up_sample(bev_for_occ)`."""
+    """HEAD:557-560 `self.up_sample(bev_for_occ)` on the product path: CUDA tensors only, like every other op of the
+    package (`up_sample_lattice` is what the CPU tests call to pin the algebra)."""
+    if not x.is_cuda:
+        from ._lib import VerError
+        raise VerError('vln_ver_b200.upsample.up_sample needs a CUDA tensor (no CPU fallback on the product path)')
     dtype = dtype or x.dtype
-    how = pick_execution(dtype, x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4], x.is_cuda)
-    return {'dense': up_sample_dense, 'gemm': up_sample_gemm, 'lattice': up_sample_lattice}[how](x, convs, dtype)
+    how = pick_execution(dtype, x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4])
+    return {'dense': up_sample_dense, 'gemm': up_sample_gemm}[how](x, convs, dtype)
