@@ -15,6 +15,8 @@ reference at docs/install.md:27-33; source NOT under /root/reference):
   * build_norm_layer(dict(type='LN'), C) = nn.LayerNorm(C, eps=1e-5)
   * mmdet FocalLoss(use_sigmoid=True) CPU path (py_sigmoid_focal_loss)
   * mmdet DETRHead.__init__ (only what VoxelFormerOccupancyHead relies on)
+  * MultiheadAttention wrapper                      (mmcv/cnn/bricks/transformer.py); DetrTransformerDecoderLayer
+    is built on the REFERENCE's own copy of BaseTransformerLayer (register_detr_decoder_layer)
 """
 import copy
 import importlib.util

@@ -17,6 +17,11 @@ Pinning status (see tests/test_oracle_pins_reference.py, oracle/gen_golden.py):
   * refine_occ (default-branch) head tail, focal loss (mmdet 2.14 FocalLoss CPU path),
     occupancy decode: restated; the reference ships no test for them ("parity
     unpinned" by the reference itself).
+  * SURVEY 8(f) N2/N3 (bottom of this file): the 3-D sampler is the reference's own function
+    (bit-equal, values and gradients); VoxelCustomMSDeformableAttention, VoxelDetectionTransformerDecoder,
+    VoxelTemporalSelfAttention and the head's detection tail are pinned against the unmodified classes
+    (tests/golden/decoder_c64.npz, head_detection_c32.npz); mmcv's MultiheadAttention wrapper is
+    third-party (mmcv-full==1.4.0) and restated.
 
 Batched semantics: the reference only runs bs=1.  For B>1 the oracle
 is "run the bs=1 reference on each panorama with its own camera matrices and
