@@ -82,9 +82,28 @@ def test_getbev_export_matches_the_reference_reinterpretation(tmp_path):
         assert np.array_equal(out[m['sample_idx']], ref)
 
 
-def test_h5py_absence_is_reported_not_papered_over():
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(ImportError, match='h5py'):
-            ingest.ViewFeatureStore(pinned=False).get('nope.h5', 'k')
+def test_feature_file_and_getbev_export_through_real_hdf5_files(tmp_path):
+    """end to end through the default opener (h5py if installed, else vln_ver_b200.h5min): a feature file with the
+    reference's layout is written, read back by ViewFeatureStore, and a getbev export is appended twice."""
+    from vln_ver_b200.ingest import _open_h5
+    rng = np.random.default_rng(1)
+    feats = {k: rng.standard_normal((1, 197, 16)).astype(np.float16) for k in ingest.view_keys('scanA_vp0', 18)}
+    fpath = str(tmp_path / 'feats.hdf5')
+    with _open_h5(fpath, 'w') as f:
+        for k, v in feats.items():
+            f.create_dataset(k, data=v)
+    store = ingest.ViewFeatureStore(pinned=False)
+    batch = store.batch([dict(file_name=fpath, sample_idx='scanA_vp0')], num_cams=18)
+    assert batch.shape == (18, 1, 196, 16)
+    assert torch.equal(batch[7, 0], torch.from_numpy(feats['scanA_vp0_i1_1'][0, 1:].astype(np.float32)))
+    C, Z, H, W = 8, 2, 3, 3
+    bpath = str(tmp_path / 'bev.hdf5')
+    bev0, bev1 = torch.randn(Z * H * W, 1, C), torch.randn(Z * H * W, 1, C)
+    ingest.export_bev_embed(bpath, [dict(sample_idx='scanA_vp0')], bev0, C, Z, H, W)
+    ingest.export_bev_embed(bpath, [dict(sample_idx='scanA_vp1')], bev1, C, Z, H, W)      # HEAD:628-629: append
+    with _open_h5(bpath, 'r') as f:
+        assert sorted(f.keys()) == ['scanA_vp0', 'scanA_vp1']
+        for key, bev in (('scanA_vp0', bev0), ('scanA_vp1', bev1)):
+            got = np.asarray(f[key])
+            assert got.dtype == np.float64 and got.shape == (C, Z, H, W)
+            assert np.array_equal(got, bev.contiguous().view(1, C, Z, H, W).squeeze().double().numpy())

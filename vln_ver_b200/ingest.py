@@ -71,12 +71,14 @@ def view_keys(sample_idx, num_cams=6):
 
 
 def _open_h5(path, mode='r'):
+    """h5py.File when h5py is installed, otherwise vln_ver_b200.h5min.File (the subset of the container format
+    these two files use: root-group datasets, contiguous or gzip-chunked, fp16 / fp32 / fp64)."""
     try:
         import h5py
-    except ImportError as e:       # the container format is h5py's; nothing here re-implements it
-        raise ImportError('reading / writing the reference\'s HDF5 feature files needs h5py '
-                          '(not installed in this environment); pass `opener=` to use another container') from e
-    return h5py.File(path, mode)
+        return h5py.File(path, mode)
+    except ImportError:
+        from . import h5min
+        return h5min.File(path, mode)
 
 
 class ViewFeatureStore:
