@@ -1,6 +1,5 @@
 """CPU tier: the oracle restatement (oracle/ver_ref.py) against the committed golden
 vectors that oracle/gen_golden.py produced from the UNMODIFIED reference."""
-import numpy as np
 import torch
 
 from oracle import ver_ref

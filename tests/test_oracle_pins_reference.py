@@ -1,9 +1,7 @@
 """CPU tier, build container only: re-runs the UNMODIFIED reference (imported from
 /root/reference through oracle/mmcv_shim.py) and checks that (a) the committed golden
 fixtures are what the reference produces and (b) the oracle restatement agrees with it."""
-import os
 
-import numpy as np
 import pytest
 import torch
 

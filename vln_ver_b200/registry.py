@@ -10,7 +10,6 @@ xavier/constant init, ConfigDict) are provided here with mmcv 1.4.0 behaviour.
 """
 import copy
 import math
-import sys
 
 import torch.nn as nn
 
