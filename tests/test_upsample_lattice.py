@@ -127,3 +127,69 @@ def test_dense_execution_and_the_choice_between_them():
     assert pick_execution(torch.float32, 900) == 'gemm'
     assert pick_execution(torch.float16, 900) == 'dense'                   # one shipped-size panorama
     assert pick_execution(torch.float16, 8 * 900) == 'gemm'
+
+
+# ------------------------------------------------------------------ occ_proj on the reinterpreted volume
+@pytest.mark.parametrize('C,Z,H,W,out_f', [(12, 4, 3, 3, 10), (24, 2, 3, 6, 7)])
+def test_occ_proj_from_lattice_equals_the_reinterpreted_dense_linear(C, Z, H, W, out_f):
+    """HEAD:564-572 on the up-sampled volume (raw .view to (Z, X, Y, C), permute, flatten, Linear) against the
+    lattice evaluation that never builds the volume: values and every gradient in fp64."""
+    import torch.nn.functional as F
+    from vln_ver_b200.upsample import occ_proj_from_lattice
+    convs = stack(C, seed=9)
+    torch.manual_seed(1)
+    lin = nn.Linear(Z * C, out_f).double()
+    x = torch.randn(2, C, Z, H, W, dtype=torch.float64, requires_grad=True)
+    Xo, Yo = 8 * H, 8 * W
+    ref = F.linear(convs(x).contiguous().view(2, Z, Xo, Yo, C).permute(0, 2, 3, 1, 4).flatten(3), lin.weight, lin.bias)
+    e, b = up_sample_lattice(x, convs, assemble=False)
+    y = occ_proj_from_lattice(e, b, lin.weight, lin.bias, Xo, Yo)
+    assert y.shape == ref.shape and (ref - y).abs().max().item() < 1e-13
+    g = torch.randn_like(ref)
+    params = [x, lin.weight, lin.bias] + list(convs.parameters())
+    for a, c in zip(torch.autograd.grad(y, params, g), torch.autograd.grad(ref, params, g)):
+        assert (a - c).abs().max().item() < 1e-12 * max(1.0, c.abs().max().item())
+
+
+def test_occ_proj_plan_at_the_shipped_shape():
+    """vocc.py: 768 channels, 4 x 120 x 120 after up-sampling, rows of 4 x 768 inputs: five data patterns (y mod 5)
+    with 720 / 768 / 816 data positions -- a quarter of the dense GEMM."""
+    from vln_ver_b200.upsample import _occ_proj_plan, occ_proj_plan_supported
+    assert occ_proj_plan_supported(768, 4, 120, 120, 120, 120)
+    assert not occ_proj_plan_supported(768, 2, 24, 24, 24, 24)          # runs would straddle channels
+    groups, chan = _occ_proj_plan(768, 4, 120, 120, 120, 120, 'cpu')
+    assert sorted(len(c) for _, c, _ in groups) == [720, 720, 768, 816, 816]
+    assert all(len(r) == 2880 for r, _, _ in groups) and chan.shape == (14400, 4)
+    for r, _, _ in groups:
+        assert len(set((r % 120 % 5).tolist())) == 1                     # a pattern is a residue of y mod 5
+
+
+def test_head_tail_modes_agree_with_the_oracle_on_cpu(monkeypatch):
+    """The shipped head tail (HEAD:551-580) through every CPU-runnable combination of up_sample_mode /
+    occ_proj_mode against the oracle.  The head's LayerNorm goes through the CUDA library on the product path;
+    here -- test only -- it is replaced by torch's so the host logic can run on CPU tensors."""
+    import torch.nn.functional as F
+    import vln_ver_b200 as V
+    from oracle import ver_ref
+    from vln_ver_b200.modules import voxelformer_occupancy_head as H
+    monkeypatch.setattr(H, 'apply_layernorm', lambda ln, y: F.layer_norm(y, ln.normalized_shape, ln.weight, ln.bias, ln.eps))
+    grid = (4, 3, 3)
+    cfg = V.vocc_head_cfg(*grid, num_cams=6, embed_dims=768, only_occ=False, refine_occ=True,
+                          occupancy_size=[0.5, 0.5, 0.5], occ_dims=8, num_layers=1, with_decoder=False)
+    torch.manual_seed(3)
+    head = V.build_head(cfg).eval()
+    with torch.no_grad():
+        for p in head.up_sample.parameters():
+            p.mul_(0.5)
+    assert (head.occ_xdim, head.occ_ydim, head.occ_zdim) == (24, 24, 7)
+    bev = torch.randn(2, 36, 768)
+    sd = {k: v.detach() for k, v in head.state_dict().items()}
+    with torch.no_grad():
+        ref = ver_ref.occ_head(sd, '', bev, *grid, 24, 24, 7, occ_dims=8, refine_occ=True, only_occ=False)
+        outs = {}
+        for up, occ in (('dense', 'dense'), ('lattice', 'dense'), ('lattice', 'lattice')):
+            head.up_sample_mode, head.occ_proj_mode = up, occ
+            outs[up, occ] = head._occupancy_tail(bev, 2)
+    for k, y in outs.items():
+        assert y.shape == ref.shape == (2, 7 * 24 * 24, 16)
+        assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-4, k

@@ -31,8 +31,9 @@ def main():
             l2i, sh = torch.from_numpy(l2i).cuda(), torch.from_numpy(sh).cuda()
             res = {}
             outs = {}
-            for mode in ('dense', 'auto'):
-                head.up_sample_mode = mode
+            for mode in ('dense', 'auto', 'gemm+occ_lattice'):
+                head.up_sample_mode = 'gemm' if '+' in mode else mode
+                head.occ_proj_mode = 'lattice' if '+' in mode else 'dense'
 
                 def run():
                     with torch.no_grad():
@@ -55,6 +56,9 @@ def main():
             print(json.dumps({'workload': 'shipped vocc.py head, inference forward', 'dtype': str(dtype).split('.')[-1],
                               'batch': bs, 'ms_up_sample_as_written': round(res['dense'], 3),
                               'ms_lattice_form': round(res['auto'], 3),
+                              'ms_gemm_up_sample_and_lattice_occ_proj': round(res['gemm+occ_lattice'], 3),
+                              'occ_lattice_max_rel_diff': (outs['gemm+occ_lattice']['occupancy_preds']
+                                                           - outs['dense']['occupancy_preds']).abs().max().item() / ref,
                               'panoramas_per_s_as_written': round(bs / res['dense'] * 1e3, 1),
                               'panoramas_per_s_lattice': round(bs / res['auto'] * 1e3, 1),
                               'libver_launches_per_forward': launches,

@@ -15,7 +15,8 @@ import torch.nn as nn
 from .. import ops
 from ..registry import (HAVE_MMCV, HEADS, LOSSES, BaseModule, bias_init_with_prob,
                         build_loss, build_positional_encoding, build_transformer)
-from ..upsample import lattice_supported, up_sample, up_sample_gemm, up_sample_lattice
+from ..upsample import (lattice_supported, occ_proj_from_lattice, occ_proj_plan_supported, up_sample, up_sample_gemm,
+                        up_sample_lattice)
 from .precision import PrecisionMixin
 from .voxel_decoder import inverse_sigmoid
 from .voxel_encoder import apply_layernorm
@@ -83,6 +84,9 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         # 'auto': lattice form (GEMM + col2im kernel on CUDA); 'gemm' / 'lattice': force one execution of it;
         # 'dense': the three ConvTranspose3d as written (A/B switch for tests and tools/upsample_bench.py)
         self.up_sample_mode = 'auto'
+        # 'lattice': occ_proj straight from the lattice data, skipping the bias constants (upsample.occ_proj_from_lattice;
+        # pinned in fp64 on CPU, not yet measured on the GPU -> off by default)
+        self.occ_proj_mode = 'dense'
         self.getbev = getbev
         self.with_box_refine, self.as_two_stage = with_box_refine, as_two_stage
         self.num_classes, self.in_channels, self.num_query = num_classes, in_channels, num_query
@@ -180,6 +184,16 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         if self.refine_occ and not self.only_occ and not self.add_layout:
             x = x.view(bs, C, self.bev_z, self.bev_h, self.bev_w)
             w_dtype = cd
+            if (self.occ_proj_mode == 'lattice' and self.bev_z != self.occ_zdim and lattice_supported(self.up_sample)
+                    and self.up_sample_mode != 'dense'
+                    and occ_proj_plan_supported(C, self.bev_z, 8 * self.bev_h, 8 * self.bev_w, self.occ_xdim,
+                                                self.occ_ydim)):
+                fn = up_sample_lattice if self.up_sample_mode == 'lattice' else up_sample_gemm
+                e, last_bias = fn(x, self.up_sample, dtype=w_dtype, assemble=False)
+                occ = occ_proj_from_lattice(e, last_bias, self.occ_proj.weight, self.occ_proj.bias, self.occ_xdim,
+                                            self.occ_ydim, dtype=w_dtype)
+                occ = occ.view(bs, self.occ_xdim, self.occ_ydim, self.occ_zdim, self.occ_dims).permute(0, 3, 1, 2, 4)
+                return self._occ_branches_tail(occ.reshape(bs, -1, self.occ_dims), cd)
             mode = self.up_sample_mode if lattice_supported(self.up_sample) else 'dense'
             if mode != 'dense':
                 # same values with 3.5x fewer FLOPs: the data of every layer lives on the even-even
@@ -202,7 +216,10 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
             x = x.permute(0, 2, 3, 1, 4).flatten(3)
             occ = self._linear(x, self.occ_proj, cd)
             occ = occ.view(bs, lat[0], lat[1], self.occ_zdim, self.occ_dims).permute(0, 3, 1, 2, 4)
-        y = occ.reshape(bs, -1, self.occ_dims)
+        return self._occ_branches_tail(occ.reshape(bs, -1, self.occ_dims), cd)
+
+    def _occ_branches_tail(self, y, cd):
+        """occ_branches (HEAD:242-248, applied at :580) on (bs, voxels, occ_dims)."""
         for layer in self.occ_branches:
             if isinstance(layer, nn.Linear):
                 y = self._linear(y, layer, cd)

@@ -48,8 +48,10 @@ def lattice_supported(convs):
         return False
 
 
-def up_sample_lattice(x, convs, dtype=None):
-    """x (bs, C, Z, H, W) -> (bs, C, Z, 2^L H, 2^L W), equal to nn.Sequential(*convs)(x)."""
+def up_sample_lattice(x, convs, dtype=None, assemble=True):
+    """x (bs, C, Z, H, W) -> (bs, C, Z, 2^L H, 2^L W), equal to nn.Sequential(*convs)(x).
+    assemble=False: return (e, bias) instead -- the last layer's lattice data (bs, C, Z, 2^(L-1) H, 2^(L-1) W)
+    and its bias, i.e. the dense result is bias everywhere plus e on the even-even lattice."""
     dtype = dtype or x.dtype
     acc = torch.float64 if dtype == torch.float64 else torch.float32      # precision of the bias-field constants
     e = x.to(dtype)
@@ -71,6 +73,8 @@ def up_sample_lattice(x, convs, dtype=None):
             c = F.conv_transpose3d(ones, u, None, stride=1, padding=(2, 2, 2), dilation=(2, 1, 1))
             e = e + c.to(dtype)
         prev_bias = b
+    if not assemble:
+        return e, prev_bias
     bs, C, Z, H, W = e.shape
     out = prev_bias.to(dtype).view(1, C, 1, 1, 1).expand(bs, C, Z, 2 * H, 2 * W).contiguous()
     out[:, :, :, 0::2, 0::2] += e
@@ -103,8 +107,8 @@ def _weight_matrix(weight, dtype):
     return hit[1]
 
 
-def up_sample_gemm(x, convs, dtype=None, col2im=None):
-    """Same contract as up_sample_lattice; GEMM + col2im execution (CUDA).  `col2im(cols, Z, Hi, Wi, s)` defaults to
+def up_sample_gemm(x, convs, dtype=None, col2im=None, assemble=True):
+    """Same contract as up_sample_lattice (including assemble=False); GEMM + col2im execution (CUDA).  `col2im(cols, Z, Hi, Wi, s)` defaults to
     the libver_b200 kernel; tests inject a torch restatement to check the algebra on CPU."""
     if col2im is None:
         from . import ops
@@ -126,6 +130,8 @@ def up_sample_gemm(x, convs, dtype=None, col2im=None):
             e = e + _bias_field_response(conv, prev_bias, Z, H, W, acc, e.device).to(dtype)
         prev_bias = conv.bias if conv.bias is not None else conv.weight.new_zeros(cout)
     C = e.shape[-1]
+    if not assemble:
+        return e.view(bs, Z, H, W, C).permute(0, 4, 1, 2, 3), prev_bias
     out = prev_bias.to(dtype).view(1, C, 1, 1, 1).expand(bs, C, Z, 2 * H, 2 * W).contiguous()
     out[:, :, :, 0::2, 0::2] += e.view(bs, Z, H, W, C).permute(0, 4, 1, 2, 3)
     return out
@@ -162,3 +168,75 @@ def up_sample(x, convs, dtype=None):
     dtype = dtype or x.dtype
     how = pick_execution(dtype, x.shape[0] * x.shape[2] * x.shape[3] * x.shape[4])
     return {'dense': up_sample_dense, 'gemm': up_sample_gemm}[how](x, convs, dtype)
+
+
+# --------------------------------------------------------------------------- occ_proj on the reinterpreted volume
+_OCC_PLAN_CACHE = {}
+
+
+def _occ_proj_plan(C, Z, Hf, Wf, Xo, Yo, device):
+    """Index plan of HEAD:564-572 for an up-sampled volume (C, Z, Hf, Wf) that is bias everywhere except on the
+    even-even lattice.  HEAD:564 REINTERPRETS that memory as (Z, Xo, Yo, C); row (x, y) of the permuted /
+    flattened tensor (:570) is the concatenation over z' of the C-element run starting at flat offset
+    ((z' Xo + x) Yo + y) C.  Returns, per distinct data pattern: the rows that have it, the positions inside the
+    Z*C-wide row that carry data, and for each (row, position) the flat index into the lattice tensor
+    (C, Z, Hf/2, Wf/2); plus, for every (row, z'), the channel whose bias fills the run."""
+    key = (C, Z, Hf, Wf, Xo, Yo, str(device))
+    if key in _OCC_PLAN_CACHE:
+        return _OCC_PLAN_CACHE[key]
+    V = Z * Hf * Wf
+    if not occ_proj_plan_supported(C, Z, Hf, Wf, Xo, Yo):
+        raise ValueError('occ_proj lattice plan: a C-element run must stay inside one channel of the volume')
+    rows = torch.arange(Xo * Yo)
+    rho = torch.arange(Z)[None, :] * (Xo * Yo) + rows[:, None]                    # (rows, Z) run index
+    chan = rho // (V // C)                                                        # bias channel of each run
+    start = (rho % (V // C)) * C                                                  # offset of the run inside its channel
+    j = torch.arange(C)
+    off = start[:, :, None] + j[None, None, :]                                    # (rows, Z, C) offset inside the channel
+    z, rem = off // (Hf * Wf), off % (Hf * Wf)
+    h, w = rem // Wf, rem % Wf
+    data = (h % 2 == 0) & (w % 2 == 0)                                            # (rows, Z, C)
+    src = ((chan[:, :, None] * Z + z) * (Hf // 2) + h // 2) * (Wf // 2) + w // 2  # index into (C, Z, Hf/2, Wf/2)
+    data2 = data.reshape(len(rows), Z * C)
+    src2 = src.reshape(len(rows), Z * C)
+    # group rows by their data pattern (at the vocc.py shape: y mod 5, five patterns of 180-204 positions per run)
+    patterns, inverse = torch.unique(data2, dim=0, return_inverse=True)
+    groups = []
+    for p in range(patterns.shape[0]):
+        r = torch.nonzero(inverse == p)[:, 0]
+        cols = torch.nonzero(patterns[p])[:, 0]
+        groups.append((r.to(device), cols.to(device), src2[r][:, cols].to(device)))
+    plan = (groups, chan.to(device))
+    _OCC_PLAN_CACHE[key] = plan
+    return plan
+
+
+def occ_proj_plan_supported(C, Z, Hf, Wf, Xo, Yo):
+    """a C-element run of the reinterpreted memory must stay inside one channel of the (C, Z, Hf, Wf) volume"""
+    return (Z * Hf * Wf) % C == 0 and Xo * Yo == Hf * Wf and Hf % 2 == 0 and Wf % 2 == 0
+
+
+def occ_proj_from_lattice(e, last_bias, weight, bias, Xo, Yo, dtype=None):
+    """`occ_proj` of HEAD:564-572 applied to the up-sampled volume WITHOUT materialising it:
+    equals  F.linear(X.view(bs, Z, Xo, Yo, C).permute(0, 2, 3, 1, 4).flatten(3), weight, bias)  for
+    X = last_bias + (e on the even-even lattice), e (bs, C, Z, Hf/2, Wf/2) from up_sample_*(assemble=False).
+    Three quarters of every input row are bias constants: their contribution is a per-run scalar times the row sums
+    of a weight block, and the GEMM runs on the data positions only (K = 720-816 instead of 3072 at the vocc.py
+    shape).  Returns (bs, Xo, Yo, out_features)."""
+    dtype = dtype or e.dtype
+    acc = torch.float64 if dtype == torch.float64 else torch.float32
+    bs, C, Z, H2, W2 = e.shape
+    groups, chan = _occ_proj_plan(C, Z, 2 * H2, 2 * W2, Xo, Yo, e.device)
+    out_f = weight.shape[0]
+    # constant part: sum over z' of last_bias[channel of the run] * (sum of the weight block's columns)
+    wsum = weight.to(acc).view(out_f, Z, C).sum(-1)                               # (out, Z)
+    const = last_bias.to(acc)[chan] @ wsum.t()                                    # (rows, out)
+    if bias is not None:
+        const = const + bias.to(acc)
+    out = const.to(dtype).unsqueeze(0).repeat(bs, 1, 1)                           # (bs, rows, out)
+    e_flat = e.reshape(bs, -1).to(dtype)
+    wt = weight.to(dtype).t()                                                     # (Z*C, out)
+    for r, cols, src in groups:
+        vals = e_flat[:, src.reshape(-1)].view(bs, src.shape[0], src.shape[1])    # (bs, rows_p, K_p)
+        out[:, r] += vals @ wt[cols]
+    return out.view(bs, Xo, Yo, out_f)
