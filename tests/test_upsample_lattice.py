@@ -193,3 +193,26 @@ def test_head_tail_modes_agree_with_the_oracle_on_cpu(monkeypatch):
     for k, y in outs.items():
         assert y.shape == ref.shape == (2, 7 * 24 * 24, 16)
         assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-4, k
+
+
+def test_head_tail_without_refine_matches_the_golden_fixture_on_cpu(monkeypatch):
+    """the only_occ head tail (the bench / smoke path: per-voxel occ_proj and the column occ_proj branch) against the
+    fixture from the unmodified reference head, run on CPU with the LayerNorm swapped for torch's (test only)."""
+    import torch.nn.functional as F
+    import vln_ver_b200 as V
+    from vln_ver_b200.config import per_voxel_occupancy_size
+    from vln_ver_b200.modules import voxelformer_occupancy_head as H
+    from conftest import load_golden, rel_err, sub
+    monkeypatch.setattr(H, 'apply_layernorm', lambda ln, y: F.layer_norm(y, ln.normalized_shape, ln.weight, ln.bias, ln.eps))
+    g = load_golden('head.npz')
+    for tag in ('pervoxel', 'column'):
+        c, sd = sub(g, tag), sub(g, tag + '.sd')
+        grid = tuple(c['grid'].tolist())
+        osz = per_voxel_occupancy_size(*grid) if tag == 'pervoxel' else [2.0, 2.0, 0.5]
+        cfg = V.vocc_head_cfg(*grid, num_cams=6, embed_dims=32, only_occ=True, refine_occ=False,
+                              occupancy_size=osz, occ_dims=16, num_layers=1)
+        head = V.build_head(cfg).eval()
+        head.load_state_dict(sd, strict=False)
+        with torch.no_grad():
+            y = head._occupancy_tail(c['bev_embed'], 1)
+        assert rel_err(y, c['occupancy_preds']) < 1e-5
