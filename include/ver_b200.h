@@ -177,11 +177,15 @@ int ver_visibility_order(const uint32_t* vis_bits, int B, int Nq, int32_t* order
 
 /* ver_sca_forward on visibility-sorted rows (fp16 tcgen05 operand images from ver_value_image_f16):
  * same result, slots written at their voxel positions.  Requires Ncam <= 32, NP in {4, 8}, S <= 256,
- * Dh in {32, 64, 96, 128}. */
+ * Dh in {32, 64, 96, 128}.
+ *   variant    0 = the fastest measured kernel generation that covers the shape (what the product passes:
+ *              sca_fwd_tc4_kernel, else sca_fwd_tc3_kernel);
+ *              3 / 4 / 5 = force sca_fwd_tc3 / tc4 / tc5_kernel (A/B timing and cross-checks in tests/, tools/;
+ *              a forced generation that does not cover the shape falls through to the next older one) */
 int ver_sca_forward_sorted(const void* vimg, const float* logits, int ld_logits, const float* rpc,
                            const int32_t* order, const uint32_t* smask, const uint32_t* tile_union,
                            void* slots, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
-                           ver_stream_t stream);
+                           int variant, ver_stream_t stream);
 
 /* Backward of ver_sca_forward.
  *   grad_slots  [B, Nq, NH*Dh] dtype

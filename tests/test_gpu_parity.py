@@ -562,7 +562,7 @@ def _offset_grad_comparable(rpc, mask, logits, B, ncam, Nq, NH, NP=8, S=14, eps=
     return full
 
 
-@pytest.mark.parametrize('fwd', ['sorted', 'sorted3', 'block'])
+@pytest.mark.parametrize('fwd', ['sorted', 'sorted5', 'sorted3', 'block'])
 @pytest.mark.parametrize('Dh,grid,B', [(96, (8, 20, 20), 2), (32, (3, 5, 7), 2), (64, (4, 8, 8), 1), (96, (3, 11, 13), 3)])
 def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B, fwd, monkeypatch):
     from vln_ver_b200._lib import lib as _l
@@ -694,7 +694,7 @@ def test_full_size_properties():
     # the tensor-core samplers (visibility-sorted rows / voxel blocks) agree with the gather at full size,
     # are linear in `value`, write exact zeros for invisible voxels and are run-to-run deterministic
     v1h = v1.half().view(B * ncam, 196, 768)
-    for fwd in ('sorted', 'sorted3', 'block'):
+    for fwd in ('sorted', 'sorted5', 'sorted3', 'block'):
         ops.TC_FORWARD = fwd
         try:
             t1 = ops.sca_sample_tc(v1h, logits, vis, 14, 14, 8, 8)

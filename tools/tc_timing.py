@@ -50,16 +50,25 @@ def main():
     vimg = ops.value_image(value, NH)
     slots = torch.empty((B, Nq, NH * Dh), dtype=torch.float16, device='cuda')
 
+    cur = [0]
+
     def launch3():
         _lib.check(_lib.lib.ver_sca_forward_sorted(vimg.data_ptr(), logits.data_ptr(), 192, rpc.data_ptr(),
                                                    order.data_ptr(), smask.data_ptr(), tu.data_ptr(),
-                                                   slots.data_ptr(), B, ncam, Nq, 14, 14, NH, Dh, 8,
+                                                   slots.data_ptr(), B, ncam, Nq, 14, 14, NH, Dh, 8, cur[0],
                                                    torch.cuda.current_stream().cuda_stream))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     ref_out = None
-    for variant, kname, tname, names in ((0, 'sca_fwd_tc4_kernel', 'ver_debug_tc4_timing', names4),
-                                         (3, 'sca_fwd_tc3_kernel', 'ver_debug_tc3_timing', names3)):
-        _lib.lib.ver_debug_sorted_variant(variant)
+    names5 = {0: 'W: setup', 1: 'W: item top (slot, prefetch, softmax)', 4: 'W: taps (arithmetic + RMW)',
+              2: 'W: wait operand free (MMA J-3)', 5: 'W: copy issue scratch->TMEM + un-tap', 6: 'W: st drain + arrive',
+              7: 'W: tail', 9: 'C: wait built', 10: 'C: wait V', 13: 'C: wait drained accumulator', 11: 'C: MMA issue',
+              12: 'C: V buffer wait + TMA', 16: 'E: wait full accumulator', 17: 'E: TMEM->slots'}
+    variants = [(5, 'sca_fwd_tc5_kernel', 'ver_debug_tc5_timing', names5),
+                (4, 'sca_fwd_tc4_kernel', 'ver_debug_tc4_timing', names4)]
+    if '--tc3' in sys.argv:
+        variants.append((3, 'sca_fwd_tc3_kernel', 'ver_debug_tc3_timing', names3))
+    for variant, kname, tname, names in variants:
+        cur[0] = variant
         f3 = hook(tname)
         for _ in range(3):
             launch3()
@@ -68,7 +77,7 @@ def main():
             ref_out = slots.clone()
         else:
             d = (slots.float() - ref_out.float()).abs().max().item() / ref_out.float().abs().max().item()
-            print(f'  max |tc3 - tc4| / max |tc4| = {d:.2e}')
+            print(f'  max |this - tc5| / max |tc5| = {d:.2e}')
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ts = []
         for i in range(10):
@@ -91,7 +100,6 @@ def main():
             print(f'  [{i:2d}] {names[i]:40s} {out3[i] / nct:10.0f}')
         print(f'  worker total {sum(out3[i] for i in range(9)) / nct:.0f}, control total '
               f'{sum(out3[i] for i in range(9, 14)) / nct:.0f}')
-    _lib.lib.ver_debug_sorted_variant(0)
     if '--fwd-only' in sys.argv:
         return
     # ---- backward: sca_bwd_tc2_kernel (two threads per hit, lane-interleaved Dots staging) vs sca_bwd_tc_kernel

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libver_b200.so')
 
 VER_F32, VER_F16 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class VerError(RuntimeError):
@@ -52,7 +52,7 @@ def _load():
         'ver_sca_backward': (c_int, [c_int, P, c_int, P, c_int, P, P, P, P, P, P, P] + [c_int] * 10 + [P]),
         'ver_visibility_order_workspace': (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),
         'ver_visibility_order': (c_int, [P, c_int, c_int, P, P, P, P, ctypes.c_size_t, P]),
-        'ver_sca_forward_sorted': (c_int, [P, P, c_int, P, P, P, P, P] + [c_int] * 8 + [P]),
+        'ver_sca_forward_sorted': (c_int, [P, P, c_int, P, P, P, P, P] + [c_int] * 9 + [P]),
         'ver_value_image_f16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
         'ver_feat_embed': (c_int, [c_int, P, P, P, P, c_int, c_int, c_int, c_int, P]),
         'ver_add_layernorm': (c_int, [c_int, P, P, P, P, P, c_int64, c_int, c_float, P]),
@@ -72,8 +72,6 @@ def _load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    lib.ver_debug_sorted_variant.restype = c_int        # debug hook (not part of the declared ABI)
-    lib.ver_debug_sorted_variant.argtypes = [c_int]
     if lib.ver_abi_version() != ABI_VERSION:
         raise VerError(f'libver_b200.so ABI {lib.ver_abi_version()} != expected {ABI_VERSION}')
     return lib, tuple(sig)

@@ -614,13 +614,6 @@ extern "C" int ver_debug_tc3_timing(int enable, unsigned long long* host_out32) 
     return VER_OK;
 }
 
-// debug: 0 = newest kernel that covers the shape (default), 3 = force sca_fwd_tc3_kernel (A/B timing in tools/)
-static int g_sorted_variant = 0;
-extern "C" int ver_debug_sorted_variant(int v) {
-    g_sorted_variant = v;
-    return VER_OK;
-}
-
 int ver_tc3_supported(int Ncam, int S, int Dh, int NP) {
     // S % 16 != 0: the padded pixel columns of the operand images double as the sink of out-of-map corners
     if (!(Ncam <= 32 && NP >= 1 && NP <= 8 && S <= 256 && S % 16 != 0 && (Dh == 32 || Dh == 64 || Dh == 96 || Dh == 128)))
@@ -633,8 +626,9 @@ int ver_tc3_supported(int Ncam, int S, int Dh, int NP) {
 extern "C" int ver_sca_forward_sorted(const void* vimg, const float* logits, int ld_logits, const float* rpc,
                                       const int32_t* order, const uint32_t* smask, const uint32_t* tile_union,
                                       void* slots, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
-                                      ver_stream_t stream) {
+                                      int variant, ver_stream_t stream) {
     VER_CHECK_ARG(vimg && logits && rpc && order && smask && tile_union && slots, "null pointer");
+    VER_CHECK_ARG(variant == 0 || (variant >= 3 && variant <= 5), "variant must be 0 (newest) or 3, 4, 5");
     VER_CHECK_ARG(B > 0 && Ncam > 0 && Nq > 0 && Sh > 0 && Sw > 0 && NH > 0, "non-positive dimension");
     VER_CHECK_ARG(ld_logits >= NH * NP * 3 && ld_logits % 4 == 0 && (NP * 2) % 4 == 0 && NP % 4 == 0,
                   "logits rows must be 16-byte aligned per head (NP %% 4 == 0, ld %% 4 == 0)");
@@ -644,7 +638,13 @@ extern "C" int ver_sca_forward_sorted(const void* vimg, const float* logits, int
     }
     const int SP = (Sh * Sw + 15) / 16 * 16;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_sorted_variant != 3 && Sh >= 2 && Sw >= 2 && ver_tc4_supported(Ncam, Sh * Sw, Dh, NP))
+    // variant 0 takes sca_fwd_tc4_kernel: the three-operand kernel measured 410-440 us against 420 us at the
+    // benchmark shape (profiles/r02b), i.e. no gain -- it stays selectable for A/B runs and as the test bed of
+    // the bounded-wait protocol
+    if (variant == 5 && Sh >= 2 && Sw >= 2 && ver_tc5_supported(Ncam, Sh * Sw, Dh, NP))
+        return ver_sca_forward_tc5(vimg, logits, ld_logits, rpc, order, smask, tile_union, slots, B, Ncam, Nq, Sh, Sw,
+                                   NH, Dh, NP, st);
+    if (variant != 3 && Sh >= 2 && Sw >= 2 && ver_tc4_supported(Ncam, Sh * Sw, Dh, NP))
         return ver_sca_forward_tc4(vimg, logits, ld_logits, rpc, order, smask, tile_union, slots, B, Ncam, Nq, Sh, Sw,
                                    NH, Dh, NP, st);
 #define FWD3(D)                                                                                                   \

@@ -148,10 +148,9 @@ class VoxelLayerFunction(Function):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        lib.ver_debug_sorted_variant(3 if ops.TC_FORWARD == 'sorted3' else 0)
         check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
                                          _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw, NH, Dh, NP,
-                                         _stream()))
+                                         ops._SORTED_VARIANT.get(ops.TC_FORWARD, 0), _stream()))
         if prof is not None:
             e1.record()
             prof.append((e0, e1))

@@ -401,9 +401,12 @@ def value_image(value, NH):
 
 
 VER_LAYOUT_TC_IMAGE = 2
-# 'sorted': visibility-sorted rows (sca_fwd_tc4_kernel, A operand in TMEM; sca_fwd_tc3_kernel for head dims it
-# does not cover); 'sorted3': force sca_fwd_tc3_kernel (debug / A-B timing); 'block': sca_fwd_tc_kernel (4x8x8 blocks)
+# 'sorted': visibility-sorted rows, the fastest measured kernel generation that covers the shape
+# (sca_fwd_tc4_kernel); 'sorted3' / 'sorted4' / 'sorted5': force a generation (tests and tools/ A-B timing only;
+# sorted5 = sca_fwd_tc5_kernel: three A operands in TMEM, two issuing threads, bounded waits);
+# 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
 TC_FORWARD = 'sorted'
+_SORTED_VARIANT = {'sorted': 0, 'sorted3': 3, 'sorted4': 4, 'sorted5': 5}
 
 
 class SCASampleTCFunction(Function):
@@ -429,12 +432,11 @@ class SCASampleTCFunction(Function):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if TC_FORWARD in ('sorted', 'sorted3') and NP % 4 == 0 and logits.shape[1] % 4 == 0:
+        if TC_FORWARD in _SORTED_VARIANT and NP % 4 == 0 and logits.shape[1] % 4 == 0:
             order, smask, tile_union = vis.order
-            lib.ver_debug_sorted_variant(3 if TC_FORWARD == 'sorted3' else 0)
             check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
                                              _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw,
-                                             NH, Dh, NP, _stream()))
+                                             NH, Dh, NP, _SORTED_VARIANT[TC_FORWARD], _stream()))
         else:
             check(lib.ver_sca_forward(VER_F16, _ptr(vimg), VER_LAYOUT_TC_IMAGE, _ptr(logits), logits.shape[1],
                                       _ptr(vis.rpc), _ptr(vis.bits), _ptr(slots), B, Ncam, Z, H, W, Sh, Sw,
