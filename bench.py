@@ -5,13 +5,17 @@ panoramas/sec, 18-view -> voxel lift+encode; HBM GB/s of the fused sampler).
     python bench.py --gpus N --steps K --warmup W            # sm_100a arm
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
 
-Workload (BASELINE.json configs[1]): vocc.py-shaped forward + backward + AdamW step, batch 8
+Headline workload (BASELINE.json configs[1]): vocc.py-shaped forward + backward + AdamW step, batch 8
 panoramas per GPU, 18 views x 196 tokens x 768, 16x40x40 voxels, fp16 storage / fp32 accumulate,
 synthetic features + random occupancy labels, per-voxel occupancy head (SURVEY.md 8(d) "head
 consistency").  N > 1: one rank per GPU, panoramas sharded, DDP gradient all-reduce (weak scaling).
+The step is captured in a CUDA graph (vln_ver_b200/graph.py) and replayed; `--no-graph` runs it eagerly.
+After the headline line's measurements a short SWEEP over the other BASELINE configs (batch-64 inference;
+batch 16/GPU at 20^3, 40^3, 80x80x16) is run and reported under "sweep" (`--no-sweep` skips it).
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -31,6 +35,11 @@ PER_GPU_BATCH = 8
 EMBED = 768
 LOSS_SCALE = 1024.0
 METRIC = 'panoramas/sec (18-view->voxel lift+encode, fwd+bwd+optimizer step)'
+# BASELINE.json configs 3 and 5 (the headline line is config 2): (name, mode, batch/GPU, grid Z H W)
+SWEEP = [('config3 get_occ.py inference', 'infer', 64, (16, 40, 40)),
+         ('config5 train 20^3', 'train', 16, (20, 20, 20)),
+         ('config5 train 40^3', 'train', 16, (40, 40, 40)),
+         ('config5 train 80x80x16', 'train', 16, (16, 80, 80))]
 
 
 def parse():
@@ -43,14 +52,26 @@ def parse():
     ap.add_argument('--grid', type=int, nargs=3, default=list(GRID), metavar=('Z', 'H', 'W'))
     ap.add_argument('--mode', default='train', choices=['train', 'infer'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--no-sweep', action='store_true', help='skip the BASELINE config 3 / 5 sweep')
+    ap.add_argument('--sweep-steps', type=int, default=3)
     return ap.parse_args()
 
 
-def workload_name(args):
-    z, h, w = args.grid
-    what = 'fwd+bwd+AdamW' if args.mode == 'train' else 'inference fwd'
-    return (f'vocc.py {what}, batch={args.batch}/GPU, {NCAM} views x196x{EMBED}, {h}x{w}x{z} voxels, '
+def workload_name(mode, batch, grid):
+    z, h, w = grid
+    what = 'fwd+bwd+AdamW' if mode == 'train' else 'inference fwd'
+    return (f'vocc.py {what}, batch={batch}/GPU, {NCAM} views x196x{EMBED}, {h}x{w}x{z} voxels, '
             f'fp16 storage/fp32 accumulate, per-voxel occ head, synthetic')
+
+
+def load_synth():
+    """vln_ver_b200/synth.py (numpy only) WITHOUT importing the package: the reference arm must not map the
+    product's shared library."""
+    spec = importlib.util.spec_from_file_location('ver_synth', os.path.join(ROOT, 'vln_ver_b200', 'synth.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 # ----------------------------------------------------------------------------- model
@@ -79,8 +100,7 @@ def build_model(grid):
     return head
 
 
-def make_batches(n_batches, batch, grid, rank, voxel_num):
-    from vln_ver_b200 import synth
+def make_batches(synth, n_batches, batch, grid, rank, voxel_num):
     out = []
     for i in range(n_batches):
         seed = 1000 * rank + 10 * i
@@ -133,11 +153,207 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(self.samples)}
 
 
-# ----------------------------------------------------------------------------- sm_100a arm
+# ----------------------------------------------------------------------------- sampler roofline
+def hbm_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return json.load(open(path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def sampler_bytes(B, Nq, P):
+    """Algorithmic bytes per launch of the fused sampler, fp16 maps (b_v = 2), SURVEY.md 8(d) fused-SCA-level formula
+    (this is the figure `roofline.achieved` uses; DESIGN.md 3 states it) and the smaller compulsory traffic of the
+    per-voxel-logit formulation this implementation actually needs (reported next to it)."""
+    bv = 2
+    fwd = B * NCAM * 196 * EMBED * bv + P * (512 + 256) + P * 4 + B * Nq * EMBED * bv + B * Nq * 4
+    # backward: re-read value / locations / weights, read grad_out once per voxel, write grad_value (fp32 here)
+    # and the location / weight gradients (SURVEY 8(d) `bytes_bwd`, with the fused formula's per-voxel output term)
+    bwd = fwd + B * NCAM * 196 * EMBED * 4 + P * 768
+    fwd_min = B * NCAM * 208 * EMBED * bv + B * Nq * 192 * 4 + P * 8 + B * Nq * 4 + B * Nq * EMBED * bv
+    return fwd, bwd, fwd_min
+
+
+def roofline_entry(kernel, ms, algorithmic, peak, peak_src, traffic_key, extra=None):
+    if not ms:
+        return None
+    ach = algorithmic / (ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'sampler_traffic.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if traffic_key in tj:
+            traffic, traffic_src = tj[traffic_key]['dram_bytes_per_launch'], tj[traffic_key]['source']
+    r = {'bound': 'hbm', 'kernel': kernel, 'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s',
+         'frac': round(ach / peak, 4), 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+         'launch_ms': round(ms, 4), 'algorithmic_bytes': int(algorithmic)}
+    r.update(extra or {})
+    return r
+
+
+# ----------------------------------------------------------------------------- one configuration on the sm_100a arm
+class Config:
+    """model + optimizer + batches of one (mode, batch, grid) on this rank."""
+
+    def __init__(self, mode, batch, grid, dev, rank, world, local, n_pool=3):
+        import vln_ver_b200 as V
+        from vln_ver_b200 import fused_layer
+        from vln_ver_b200.ingest import pin
+        self.V, self.mode, self.batch, self.grid, self.dev = V, mode, batch, tuple(grid), dev
+        self.rank, self.world, self.ddp = rank, world, world > 1
+        self.train = mode == 'train'
+        self.Nq = grid[0] * grid[1] * grid[2]
+        head = build_model(self.grid).to(dev)
+        V.set_compute_dtype(head, torch.float16)
+        self.head = self.model = head
+        if self.train:
+            head.train()
+            if self.ddp:
+                self.model = torch.nn.parallel.DistributedDataParallel(
+                    head, device_ids=[local], gradient_as_bucket_view=True, static_graph=True)
+            self.params = [p for p in head.parameters() if p.requires_grad]
+            # vocc.py:261-268; capturable: the step counter lives on the device (CUDA-graph replay)
+            self.opt = torch.optim.AdamW(self.params, lr=1e-4, weight_decay=0.01, fused=True, capturable=True)
+            # static scale 1024 would poison AdamW on an fp16 overflow: GradScaler skips such steps on the device
+            self.scaler = torch.amp.GradScaler('cuda', init_scale=LOSS_SCALE, growth_interval=10 ** 9)
+            fused_layer.install_cache_hooks(head, self.opt)
+        else:
+            head.eval()
+        synth = load_synth()
+        self.pool_host = [pin(b) for b in make_batches(synth, n_pool, batch, self.grid, rank, head.voxel_num)]
+        self.pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in self.pool_host]
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.pool_host[0].values())
+        self.captured, self.graph_note = None, 'eager'
+
+    # ---- one pass of the hot path over one batch; returns the loss (device scalar)
+    def step(self, feats, l2i, sh, gts):
+        head, model = self.head, self.model
+        if not self.train:
+            with torch.no_grad():
+                outs = model(feats, None, lidar2img=l2i, originshift=sh)
+            return outs['occupancy_preds'].float().mean()
+        outs = model(feats, None, lidar2img=l2i, originshift=sh)
+        loss = head.loss_only_occupancy(None, None, None, list(gts), None, outs)['loss_occupancy']
+        self.opt.zero_grad(set_to_none=True)
+        self.scaler.scale(loss).backward()
+        self.scaler.unscale_(self.opt)
+        torch.nn.utils.clip_grad_norm_(self.params, 300.0)                          # vocc.py:270
+        self.scaler.step(self.opt)
+        self.scaler.update()
+        return loss.detach()
+
+    def capture(self, warmup):
+        from vln_ver_b200.graph import CapturedStep
+        try:
+            self.captured = CapturedStep(self.step, self.pool_dev[0], warmup=warmup, ddp=self.ddp and self.train)
+            self.graph_note = 'cuda graph replay'
+        except Exception as e:  # noqa: BLE001  (fall back to eager, say why)
+            self.captured = None
+            self.graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'
+            torch.cuda.synchronize()
+
+    def run(self, batch):
+        return self.captured(**batch) if self.captured is not None else self.step(**batch)
+
+    def barrier(self):
+        if self.ddp:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = torch.tensor([ms], device=self.dev)
+        if self.ddp:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return t.item()
+
+    def timed_device(self, steps, warmup):
+        """`value`: inputs resident in HBM, CUDA events around exactly `steps` steps, max over ranks."""
+        n = len(self.pool_dev)
+        for i in range(warmup):
+            self.run(self.pool_dev[i % n])
+        self.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = self.V.launch_count()
+        t0.record()
+        for i in range(steps):
+            self.run(self.pool_dev[(warmup + i) % n])
+        t1.record()
+        self.barrier()
+        launches = self.V.launch_count() - n0
+        if self.captured is not None:
+            launches = self.captured.launches_per_replay * steps
+        return self.max_over_ranks(t0.elapsed_time(t1)), launches
+
+    def timed_e2e(self, steps, warmup):
+        """`e2e`: every step's inputs start in pinned host memory and are copied inside the timed region (exactly
+        `steps` copies; vln_ver_b200.ingest.DevicePrefetcher keeps the copy of step i+1 on a side stream under the
+        compute of step i); every step's loss is read device -> host through a pinned buffer + event, one step
+        behind the launch front."""
+        from vln_ver_b200.ingest import DevicePrefetcher
+        n = len(self.pool_host)
+        loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+        def one_pass(first, count):
+            pf = DevicePrefetcher((self.pool_host[(first + j) % n] for j in range(count)), self.dev)
+            pending = None
+            for i, batch in enumerate(pf):
+                loss = self.run(batch)
+                buf = loss_host[i % 2]
+                buf.copy_(loss.detach().float().reshape(1), non_blocking=True)      # device -> host, 4 bytes
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[0].synchronize()
+                    pending[1].item()
+                pending = (ev, buf)
+            if pending is not None:
+                pending[0].synchronize()
+                pending[1].item()
+            return pf.h2d_bytes
+
+        one_pass(0, warmup)
+        self.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        copied = one_pass(warmup, steps)
+        t1.record()
+        self.barrier()
+        assert copied == self.h2d_bytes * steps
+        return self.max_over_ranks(t0.elapsed_time(t1))
+
+    def sampler_launch_ms(self, steps=3):
+        """Device duration of the fused sampler launches inside real steps: CUDA events recorded on the launching
+        stream around each launch.  Events cannot be read back from inside a replayed graph, so these are `steps`
+        EAGER steps of the same workload run right after the timed region (same model, same batches, same clocks)."""
+        from vln_ver_b200 import ops
+        fwd, bwd = [], []
+        ops.PROFILE_EVENTS, ops.PROFILE_EVENTS_BWD = fwd, bwd
+        try:
+            for i in range(steps):
+                self.step(**self.pool_dev[i % len(self.pool_dev)])
+            torch.cuda.synchronize()
+        finally:
+            ops.PROFILE_EVENTS = ops.PROFILE_EVENTS_BWD = None
+        f = float(np.mean([a.elapsed_time(b) for a, b in fwd])) if fwd else None
+        b = float(np.mean([a.elapsed_time(b) for a, b in bwd])) if bwd else None
+        return f, b
+
+    def hits_per_launch(self):
+        from vln_ver_b200 import ops
+        counts = [int(ops.point_sampling(b['l2i'], b['sh'], self.head.transformer.encoder.pc_range, *self.grid)[3]
+                      .sum().item()) for b in self.pool_dev]
+        return float(np.mean(counts))
+
+    def release(self):
+        self.captured = None
+        self.model = self.head = self.opt = self.params = self.pool_dev = self.pool_host = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
 def run_b200(args):
     import torch.distributed as dist
-    import vln_ver_b200 as V
-    from vln_ver_b200 import ops
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -145,183 +361,89 @@ def run_b200(args):
     assert world == args.gpus or world == 1, (world, args.gpus)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    ddp = world > 1
-    if ddp:
+    if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False
-    grid = tuple(args.grid)
-    Nq = grid[0] * grid[1] * grid[2]
-    train = args.mode == 'train'
+    peak, peak_src = hbm_peak()
 
-    head = build_model(grid).to(dev)
-    V.set_compute_dtype(head, torch.float16)
-    model = head
-    if train:
-        head.train()
-        if ddp:
-            model = torch.nn.parallel.DistributedDataParallel(
-                head, device_ids=[local], gradient_as_bucket_view=True, static_graph=True)
-        params = [p for p in head.parameters() if p.requires_grad]
-        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)   # vocc.py:261-268
-    else:
-        head.eval()
-
-    n_pool = 3
-    pool_host = make_batches(n_pool, args.batch, grid, rank, head.voxel_num)
-    from vln_ver_b200.ingest import pin
-    pool_host = [pin(b) for b in pool_host]
-    pool_dev = [{k: v.to(dev) for k, v in b.items()} for b in pool_host]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pool_host[0].values())
-
-    sampler_events = []
-
-    def step(batch, timed_sampler=False):
-        """one pass of the hot path over one batch; returns the loss tensor (device)."""
-        ops.PROFILE_EVENTS = sampler_events if timed_sampler else None
-        if not train:
-            with torch.no_grad():
-                outs = model(batch['feats'], None, lidar2img=batch['l2i'], originshift=batch['sh'])
-            return outs['occupancy_preds'].float().mean()
-        outs = model(batch['feats'], None, lidar2img=batch['l2i'], originshift=batch['sh'])
-        loss = head.loss_only_occupancy(None, None, None, list(batch['gts']), None, outs)['loss_occupancy']
-        opt.zero_grad(set_to_none=True)
-        (loss * LOSS_SCALE).backward()
-        torch._foreach_mul_([p.grad for p in params if p.grad is not None], 1.0 / LOSS_SCALE)
-        torch.nn.utils.clip_grad_norm_(params, 300.0)                                # vocc.py:270
-        opt.step()
-        return loss.detach()
-
-    def barrier():
-        if ddp:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(run_one, steps, warmup):
-        for i in range(warmup):
-            run_one(i)
-        barrier()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = V.launch_count()
-        t0.record()
-        for i in range(steps):
-            run_one(warmup + i)
-        t1.record()
-        barrier()
-        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
-        if ddp:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), V.launch_count() - n0
-
-    # ---- (1) device-resident inputs: `value`
+    # ---------------- headline configuration (BASELINE config 2 unless overridden on the command line)
+    cfg = Config(args.mode, args.batch, args.grid, dev, rank, world, local)
+    if not args.no_graph:
+        cfg.capture(args.warmup)
     with ClockSampler(local) as clocks:
-        ms_dev, launches = timed(lambda i: step(pool_dev[i % n_pool], timed_sampler=True),
-                                 args.steps, args.warmup)
+        ms_dev, launches = cfg.timed_device(args.steps, args.warmup)
         clk = clocks.summary()
-    ops.PROFILE_EVENTS = None
-    # sampler forward duration from the events recorded inside the timed steps
-    torch.cuda.synchronize()
-    ev = sampler_events[-3 * args.steps:] if len(sampler_events) >= 3 * args.steps else sampler_events
-    sampler_ms = float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else None
-
-    # ---- (2) end to end through the public API with HOST buffers: `e2e`
-    # every step's inputs start in pinned host memory and are copied inside the timed region (exactly K
-    # copies for K steps); vln_ver_b200.ingest.DevicePrefetcher keeps the copy of step i+1 on a side stream
-    # under the compute of step i.  Every step's loss is read device -> host inside the region.
-    from vln_ver_b200.ingest import DevicePrefetcher
-
-    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-
-    def e2e_pass(first, n):
-        """n steps from host batches; every step's loss is read back on the host through a pinned buffer
-        + event, one step behind the launch front (the host enqueues step i+1 while step i runs)."""
-        pf = DevicePrefetcher((pool_host[(first + j) % n_pool] for j in range(n)), dev)
-        pending, last = None, None
-        for i, batch in enumerate(pf):
-            loss = step(batch)
-            buf = loss_host[i % 2]
-            buf.copy_(loss.detach().float().reshape(1), non_blocking=True)      # device -> host, 4 bytes
-            ev = torch.cuda.Event()
-            ev.record()
-            if pending is not None:
-                pending[0].synchronize()
-                last = pending[1].item()
-            pending = (ev, buf)
-        if pending is not None:
-            pending[0].synchronize()
-            last = pending[1].item()
-        return pf.h2d_bytes
-
-    e2e_pass(0, args.warmup)
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    copied = e2e_pass(args.warmup, args.steps)
-    t1.record()
-    barrier()
-    assert copied == h2d_bytes * args.steps
-    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
-    if ddp:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_e2e = ms.item()
-
+    ms_e2e = cfg.timed_e2e(args.steps, args.warmup)
+    fwd_ms, bwd_ms = cfg.sampler_launch_ms() if cfg.train else (cfg.sampler_launch_ms()[0], None)
+    P = cfg.hits_per_launch()
     pano = args.batch * world * args.steps
-    value = pano / (ms_dev / 1e3)
-    e2e_value = pano / (ms_e2e / 1e3)
+    value, e2e_value = pano / (ms_dev / 1e3), pano / (ms_e2e / 1e3)
+    b_fwd, b_bwd, b_min = sampler_bytes(args.batch, cfg.Nq, P)
+    at_headline_shape = args.batch == PER_GPU_BATCH and tuple(args.grid) == GRID
+    note = ('algorithmic bytes = SURVEY.md 8(d) fused-SCA formula; the per-voxel-logit formulation needs only '
+            '`compulsory_bytes`; launch_ms = CUDA events on the launching stream around each launch inside 3 eager '
+            'steps run right after the timed (graph-replayed) region')
+    roof = roofline_entry('sca_fwd_tc4_kernel<96, 8> (tcgen05 fused SCA sampler forward, visibility-sorted rows, '
+                          'A operand in TMEM)', fwd_ms, b_fwd, peak, peak_src,
+                          'forward' if at_headline_shape else '-',
+                          {'compulsory_bytes': int(b_min), 'hits_per_launch': P, 'note': note})
+    roof_bwd = roofline_entry('sca_bwd_tc2_kernel<96, 8> (tcgen05 fused SCA sampler backward + scatter)', bwd_ms,
+                              b_bwd, peak, peak_src, 'backward' if at_headline_shape else '-',
+                              {'hits_per_launch': P})
+    max_mem_gb = round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)
+    graph_note = cfg.graph_note
+    h2d = cfg.h2d_bytes
+    cfg.release()
+
+    # ---------------- sweep: BASELINE configs 3 and 5 (short, eager or graph as the headline; same metric)
+    sweep = []
+    if not args.no_sweep:
+        for name, mode, batch, grid in SWEEP:
+            entry = {'config': name, 'workload': workload_name(mode, batch, grid)}
+            try:
+                torch.cuda.reset_peak_memory_stats(dev)
+                c = Config(mode, batch, grid, dev, rank, world, local, n_pool=2)
+                if not args.no_graph:
+                    c.capture(2)
+                ms, _ = c.timed_device(args.sweep_steps, 2)
+                f_ms, b_ms = c.sampler_launch_ms(2)
+                Pc = c.hits_per_launch()
+                bf, bb, _ = sampler_bytes(batch, c.Nq, Pc)
+                entry.update({
+                    'value': round(batch * world * args.sweep_steps / (ms / 1e3), 2), 'unit': 'panoramas/s',
+                    'ms_per_step': round(ms / args.sweep_steps, 3), 'steps': args.sweep_steps, 'execution': c.graph_note,
+                    'sampler_fwd_ms': round(f_ms, 4) if f_ms else None,
+                    'sampler_fwd_frac': round(bf / (f_ms * 1e-3) / 1e9 / peak, 4) if f_ms else None,
+                    'sampler_bwd_ms': round(b_ms, 4) if (b_ms and mode == 'train') else None,
+                    'sampler_bwd_frac': round(bb / (b_ms * 1e-3) / 1e9 / peak, 4) if (b_ms and mode == 'train') else None,
+                    'max_memory_allocated_gb': round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)})
+                c.release()
+            except Exception as e:  # noqa: BLE001  (a sweep point must not take the headline line down)
+                entry['error'] = f'{type(e).__name__}: {str(e)[:200]}'
+                torch.cuda.synchronize()
+            sweep.append(entry)
 
     result = None
     if rank == 0:
-        # ---- roofline of the fused forward sampler (dominant HBM-side kernel of the lift)
-        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
-        else:
-            peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-        counts = [int(ops.point_sampling(b['l2i'], b['sh'], head.transformer.encoder.pc_range, *grid)[3]
-                      .sum().item()) for b in pool_dev]
-        P = float(np.mean(counts))                       # visible (b, cam, voxel) pairs per launch
-        B = args.batch
-        bv = 2
-        bytes_min = (B * NCAM * 208 * EMBED * bv        # value operand images (196 px padded to 208), read once
-                     + B * Nq * 192 * 4                 # offset/weight logits, once per VOXEL
-                     + P * 8 + B * Nq * 4               # reference points per hit, visibility bits
-                     + B * Nq * EMBED * bv)             # slots written once
-        bytes_survey = (B * NCAM * 196 * EMBED * bv + P * (512 + 256) + P * 4
-                        + B * Nq * EMBED * bv + B * Nq * 4)      # SURVEY.md 8(d) fused formula
-        roof = None
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, 'profiles', 'sampler_traffic.json')
-        if os.path.exists(tpath) and args.batch == PER_GPU_BATCH and tuple(args.grid) == GRID:
-            tj = json.load(open(tpath))
-            traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
-        if sampler_ms:
-            ach = bytes_min / (sampler_ms * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': 'sca_fwd_tc4_kernel<96, 8> (tcgen05 fused SCA sampler forward, visibility-sorted rows, A operand in TMEM)',
-                    'achieved': round(ach, 1),
-                    'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4), 'traffic': traffic, 'traffic_source': traffic_src,
-                    'peak_source': peak_src, 'launch_ms': round(sampler_ms, 4),
-                    'algorithmic_bytes': int(bytes_min),
-                    'achieved_survey_formula': round(bytes_survey / (sampler_ms * 1e-3) / 1e9, 1),
-                    'hits_per_launch': P,
-                    'note': 'algorithmic bytes = compulsory traffic of the per-voxel-logit formulation '
-                            '(smaller than SURVEY 8(d) fused formula, also given); timed with CUDA events '
-                            'around the launch inside the timed steps'}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference(args, steps=1, warmup=0)
+            cpu = cpu_reference(args, steps=3, warmup=1, budget_s=90.0)
         result = {
             'metric': METRIC, 'value': round(value, 2), 'unit': 'panoramas/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms_dev / args.steps, 3),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16',
             'data': 'synthetic', 'impl': 'b200',
-            'config': {'workload': workload_name(args), 'global_batch': args.batch * world,
-                       'parallelism': f'dp{world}', 'l2': 'inputs+activations per step (>1 GB) exceed the 126 MB L2; '
-                                                         f'{n_pool} distinct batches cycled'},
-            'e2e': {'value': round(e2e_value, 2), 'unit': 'panoramas/s', 'h2d_bytes_per_step': int(h2d_bytes),
+            'config': {'workload': workload_name(args.mode, args.batch, args.grid), 'global_batch': args.batch * world,
+                       'parallelism': f'dp{world}', 'execution': graph_note,
+                       'l2': 'inputs+activations per step (>1 GB) exceed the 126 MB L2; 3 distinct batches cycled',
+                       'max_memory_allocated_gb': max_mem_gb},
+            'e2e': {'value': round(e2e_value, 2), 'unit': 'panoramas/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_e2e / args.steps, 3)},
-            'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'cpu_baseline': cpu,
+            'gpu_launches': int(launches), 'clocks': clk, 'roofline': roof, 'roofline_backward': roof_bwd,
+            'cpu_baseline': cpu, 'sweep': sweep,
         }
         print(json.dumps(result), flush=True)
-    if ddp:
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return result
@@ -331,52 +453,57 @@ def run_b200(args):
 def cpu_reference(args, steps, warmup, budget_s=240.0):
     """The reference's CPU path for the same workload, as the oracle PORT (oracle/ver_ref.py: the
     reference's PyTorch-CPU ops restated; /root/reference itself cannot travel to the GPU box).
-    One step = fwd+bwd of ONE panorama (bounded sample).  Threads: min(cores, 16) -- measured: the
-    op mix (grid_sample on padded rebatches, index_put loops) gets SLOWER beyond that (127 s/step with
-    128 threads vs 33 s with 8).  If `steps` would exceed `budget_s` the number of timed steps is cut
-    and reported."""
-    from oracle import ver_ref
-    from vln_ver_b200 import synth
+    One step = fwd+bwd of ONE panorama (bounded sample; NO optimizer step / gradient clipping, which the GPU arm's
+    step includes).  Imports nothing from the product package: the weights come from oracle/ref_init.py, the
+    synthetic inputs from vln_ver_b200/synth.py loaded as a plain file.  Threads: min(cores, 16) -- measured: the
+    op mix (grid_sample on padded rebatches, index_put loops) gets SLOWER beyond that (127 s/step with 128 threads
+    vs 33 s with 8).  If the timed steps would exceed `budget_s` their number is cut and reported."""
+    from oracle import ref_init, ver_ref
+    synth = load_synth()
     cores = os.cpu_count() or 1
     threads = min(cores, 16)
     torch.set_num_threads(threads)
     grid = tuple(args.grid)
-    head = build_model(grid)
+    z, h, w = grid
     train = args.mode == 'train'
-    sd = {k: v.detach().clone().requires_grad_(train and v.is_floating_point())
-          for k, v in head.state_dict().items()}
-    batch = make_batches(1, 1, grid, 0, head.voxel_num)[0]
+    sd = {k: v.clone().requires_grad_(train and v.is_floating_point())
+          for k, v in ref_init.lift_encode_state_dict(grid, NCAM, EMBED).items()}
+    voxel_num = z * h * w                                   # per-voxel head: occupancy grid == voxel grid
+    batch = make_batches(synth, 1, 1, grid, 0, voxel_num)[0]
 
     def one():
         with torch.set_grad_enabled(train):
             bev = ver_ref.get_voxel_features(sd, 'transformer.', batch['feats'], sd['voxel_embedding.weight'],
                                              *grid, synth.PC_RANGE, batch['l2i'], batch['sh'])
-            occ = ver_ref.occ_head(sd, '', bev, *grid, head.occ_xdim, head.occ_ydim, head.occ_zdim,
-                                   occ_dims=head.occ_dims, refine_occ=False, only_occ=True)
+            occ = ver_ref.occ_head(sd, '', bev, z, h, w, w, h, z, occ_dims=128, refine_occ=False, only_occ=True)
             if train:
                 loss = ver_ref.occupancy_loss(occ, [batch['gts'][0]])
                 loss.backward()
                 for v in sd.values():
                     v.grad = None
     tw = time.perf_counter()
+    warmed = 0
     for _ in range(warmup):
         one()
+        warmed += 1
         if time.perf_counter() - tw > budget_s / 4:       # warm-up is bounded too
             break
-    t0 = time.perf_counter()
-    done = 0
+    times = []
+    t_all = time.perf_counter()
     for _ in range(steps):
+        t0 = time.perf_counter()
         one()
-        done += 1
-        dt = time.perf_counter() - t0
-        if dt / done * (done + 1) > budget_s:
+        times.append(time.perf_counter() - t0)
+        if (time.perf_counter() - t_all) + max(times) > budget_s:
             break
-    dt = time.perf_counter() - t0
-    return {'value': round(done / dt, 4), 'unit': 'panoramas/s', 'cores': threads, 'host_cores': cores,
-            'kind': 'port', 'steps_timed': done,
-            'sample': f'{done} step(s) x 1 panorama {"fwd+bwd" if train else "fwd"} of the same model/grid '
-                      f'(oracle port of the reference PyTorch-CPU path, fp32, {threads} threads), {dt:.1f} s',
-            'ms_per_step': round(dt / done * 1e3, 1)}
+    done = len(times)
+    med = float(np.median(times))
+    return {'value': round(1.0 / med, 4), 'unit': 'panoramas/s', 'cores': threads, 'host_cores': cores,
+            'kind': 'port', 'steps_timed': done, 'warmup_steps': warmed,
+            'sample': f'median of {done} step(s) x 1 panorama {"fwd+bwd, no optimizer step" if train else "fwd"} of '
+                      f'the same model/grid (oracle port of the reference PyTorch-CPU path, fp32, {threads} threads) '
+                      f'after {warmed} warm-up step(s), {sum(times):.1f} s',
+            'ms_per_step': round(med * 1e3, 1)}
 
 
 def run_reference(args):
@@ -389,7 +516,8 @@ def run_reference(args):
         'metric': METRIC, 'value': cpu['value'], 'unit': 'panoramas/s', 'n_gpus': world, 'steps': cpu['steps_timed'],
         'warmup': args.warmup, 'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-        'config': {'workload': workload_name(args), 'global_batch': 1, 'parallelism': 'cpu'},
+        'config': {'workload': workload_name(args.mode, args.batch, args.grid), 'global_batch': 1,
+                   'parallelism': 'cpu'},
         'cpu_baseline': cpu, 'gpu_launches': 0,
         'e2e': {'value': cpu['value'], 'unit': 'panoramas/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0}}), flush=True)

@@ -219,25 +219,29 @@ int ver_add_layernorm(int dtype, const void* x, const void* residual, const floa
 /* Training forms of the same epilogue (dropout p = 0.1 in vocc.py:135 / spatial_cross_attention.py:62):
  *   z = residual + dropout(x, p) ;  y = LayerNorm(z) * gamma + beta
  * with a counter-based Philox dropout mask that backward regenerates from (seed, element index).
+ *   seed_epoch (device, may be NULL): one 64-bit word that the kernels ADD to `seed` when they run -- a step
+ *   captured in a CUDA graph bumps that word inside the graph and so draws fresh masks on every replay, while
+ *   forward and backward of one step still see the same value.
  *   z_out (dtype) and stats (float2 mean, rstd per row) are saved for backward; both may be NULL.
  * Backward: dx = dz * keep/(1-p), dresidual = dz (may be NULL), and per-block partial sums of
  *   dgamma / dbeta and, if dxsum_part != NULL, of the columns of dx (= the bias gradient of the Linear that
  *   produced x): [ver_dropout_add_layernorm_bwd_blocks(rows), C] fp32 each (caller sums over dim 0). */
 int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const void* residual, const float* gamma,
                                   const float* beta, void* y, void* z_out, float* stats, int64_t rows,
-                                  int C, float eps, float p_drop, uint64_t seed, ver_stream_t stream);
+                                  int C, float eps, float p_drop, uint64_t seed, const uint64_t* seed_epoch,
+                                  ver_stream_t stream);
 int ver_dropout_add_layernorm_bwd_blocks(int64_t rows);
 int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const void* z, const float* stats,
                                   const float* gamma, void* dx, void* dresidual, float* dgamma_part,
                                   float* dbeta_part, float* dxsum_part, int64_t rows, int C, float p_drop,
-                                  uint64_t seed, ver_stream_t stream);
+                                  uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream);
 /* FFN inner activation (mmcv FFN: Linear -> ReLU -> Dropout): h = dropout(relu(a)), in place allowed;
  * backward da = dh * [h > 0] / (1 - p).  n % 8 == 0.
  * Column sums (bias gradients) come as partial sums: colsum_part is [ver_colsum_partial_rows(), 8] fp32 and row t
  * holds partial sums of columns 8 * (t % (C / 8)) ... + 7, i.e. colsum = part.view(-1, C / 8, 8).sum(0).view(C);
  * C / 8 must divide ver_colsum_partial_rows().  colsum_part may be NULL for ver_relu_dropout_bwd (C is then unused). */
 int ver_relu_dropout_fwd(int dtype, const void* a, void* h, int64_t n, float p_drop, uint64_t seed,
-                         ver_stream_t stream);
+                         const uint64_t* seed_epoch, ver_stream_t stream);
 int ver_colsum_partial_rows(void);
 int ver_relu_dropout_bwd(int dtype, const void* dh, const void* h, void* da, int64_t n, float p_drop, int C,
                          float* colsum_part, ver_stream_t stream);

@@ -57,11 +57,11 @@ def _load():
         'ver_feat_embed': (c_int, [c_int, P, P, P, P, c_int, c_int, c_int, c_int, P]),
         'ver_add_layernorm': (c_int, [c_int, P, P, P, P, P, c_int64, c_int, c_float, P]),
         'ver_dropout_add_layernorm_fwd': (c_int, [c_int, P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float,
-                                                  ctypes.c_uint64, P]),
+                                                  ctypes.c_uint64, P, P]),
         'ver_dropout_add_layernorm_bwd_blocks': (c_int, [c_int64]),
         'ver_dropout_add_layernorm_bwd': (c_int, [c_int, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_float,
-                                                  ctypes.c_uint64, P]),
-        'ver_relu_dropout_fwd': (c_int, [c_int, P, P, c_int64, c_float, ctypes.c_uint64, P]),
+                                                  ctypes.c_uint64, P, P]),
+        'ver_relu_dropout_fwd': (c_int, [c_int, P, P, c_int64, c_float, ctypes.c_uint64, P, P]),
         'ver_colsum_partial_rows': (c_int, []),
         'ver_relu_dropout_bwd': (c_int, [c_int, P, P, P, c_int64, c_float, c_int, P, P]),
         'ver_cast_colsum': (c_int, [c_int, P, P, c_int64, c_int, P, P]),

@@ -92,7 +92,9 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 dropout_add_ln_fwd(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                    const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ z_out,
-                   float2* __restrict__ stats, int64_t rows, int C, float eps, float p, uint64_t seed) {
+                   float2* __restrict__ stats, int64_t rows, int C, float eps, float p, uint64_t seed,
+                   const unsigned long long* __restrict__ seed_epoch) {
+    if (seed_epoch) seed += *seed_epoch;        // device-side word: fresh masks on every replay of a captured graph
     // gamma / beta staged in shared memory as [lo | hi][C / 8] float4: a lane's 8 columns are two conflict-free
     // 16-byte reads.  (Reading them from global cost 32 L1 sectors per warp request -- lane stride 32 B -- and made
     // the L1 path, not HBM, the bound of this kernel: 10.7 GB of L1 traffic for 1.2 GB of DRAM traffic.)
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(256, 2)
 dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const float2* __restrict__ stats,
                    const float* __restrict__ gamma, T* __restrict__ dx, T* __restrict__ dres,
                    float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, float* __restrict__ dxsum_part,
-                   int64_t rows, int C, float p, uint64_t seed) {
+                   int64_t rows, int C, float p, uint64_t seed, const unsigned long long* __restrict__ seed_epoch) {
+    if (seed_epoch) seed += *seed_epoch;
     extern __shared__ float s_part[];       // [8 warps][C], reused for the three reductions
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t thr16 = (uint32_t)(p * 65536.f);
@@ -311,7 +314,9 @@ dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const floa
 // ---------------------------------------------------------------- h = dropout(relu(a)), in place capable
 template <typename T>
 __global__ void __launch_bounds__(256)
-relu_dropout_fwd(const T* __restrict__ a, T* __restrict__ h, int64_t n8, float p, uint64_t seed) {
+relu_dropout_fwd(const T* __restrict__ a, T* __restrict__ h, int64_t n8, float p, uint64_t seed,
+                 const unsigned long long* __restrict__ seed_epoch) {
+    if (seed_epoch) seed += *seed_epoch;
     const uint32_t thr16 = (uint32_t)(p * 65536.f);
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -407,7 +412,8 @@ int ln_grid(int64_t rows) {
 extern "C" int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const void* residual,
                                              const float* gamma, const float* beta, void* y, void* z_out,
                                              float* stats, int64_t rows, int C, float eps, float p_drop,
-                                             uint64_t seed, ver_stream_t stream) {
+                                             uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream) {
+    const unsigned long long* ep = (const unsigned long long*)seed_epoch;
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
     VER_CHECK_ARG(x && gamma && beta && y, "null pointer");
     VER_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 1024, "C must be a multiple of 8, <= 1024 (got %d)", C);
@@ -416,9 +422,9 @@ extern "C" int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const voi
     const int nv = (C + 255) / 256;
     const int grid = ln_grid(rows);
     if (dtype == VER_F16)
-        LN_DISPATCH(dropout_add_ln_fwd, __half, nv, <<<grid, 256, 0, st>>>((const __half*)x, (const __half*)residual, gamma, beta, (__half*)y, (__half*)z_out, (float2*)stats, rows, C, eps, p_drop, seed));
+        LN_DISPATCH(dropout_add_ln_fwd, __half, nv, <<<grid, 256, 0, st>>>((const __half*)x, (const __half*)residual, gamma, beta, (__half*)y, (__half*)z_out, (float2*)stats, rows, C, eps, p_drop, seed, ep));
     else
-        LN_DISPATCH(dropout_add_ln_fwd, float, nv, <<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y, (float*)z_out, (float2*)stats, rows, C, eps, p_drop, seed));
+        LN_DISPATCH(dropout_add_ln_fwd, float, nv, <<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y, (float*)z_out, (float2*)stats, rows, C, eps, p_drop, seed, ep));
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;
@@ -430,7 +436,8 @@ extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const vo
                                              const float* gamma, void* dx, void* dresidual,
                                              float* dgamma_part, float* dbeta_part, float* dxsum_part,
                                              int64_t rows, int C, float p_drop, uint64_t seed,
-                                             ver_stream_t stream) {
+                                             const uint64_t* seed_epoch, ver_stream_t stream) {
+    const unsigned long long* ep = (const unsigned long long*)seed_epoch;
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
     VER_CHECK_ARG(dy && z && stats && gamma && dx && dgamma_part && dbeta_part, "null pointer");
     VER_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 1024, "C must be a multiple of 8, <= 1024 (got %d)", C);
@@ -443,13 +450,13 @@ extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const vo
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        LN_DISPATCH(dropout_add_ln_bwd, __half, nv, <<<grid, 256, smem, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed));
+        LN_DISPATCH(dropout_add_ln_bwd, __half, nv, <<<grid, 256, smem, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep));
     } else {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(dropout_add_ln_bwd<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(dropout_add_ln_bwd<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        LN_DISPATCH(dropout_add_ln_bwd, float, nv, <<<grid, 256, smem, st>>>((const float*)dy, (const float*)z, (const float2*)stats, gamma, (float*)dx, (float*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed));
+        LN_DISPATCH(dropout_add_ln_bwd, float, nv, <<<grid, 256, smem, st>>>((const float*)dy, (const float*)z, (const float2*)stats, gamma, (float*)dx, (float*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep));
     }
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
@@ -457,14 +464,15 @@ extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const vo
 }
 
 extern "C" int ver_relu_dropout_fwd(int dtype, const void* a, void* h, int64_t n, float p_drop, uint64_t seed,
-                                    ver_stream_t stream) {
+                                    const uint64_t* seed_epoch, ver_stream_t stream) {
+    const unsigned long long* ep = (const unsigned long long*)seed_epoch;
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
     VER_CHECK_ARG(a && h && n > 0 && n % 8 == 0, "bad arguments (n %% 8 != 0?)");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n8 = n / 8;
     const int grid = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
-    if (dtype == VER_F16) relu_dropout_fwd<__half><<<grid, 256, 0, st>>>((const __half*)a, (__half*)h, n8, p_drop, seed);
-    else relu_dropout_fwd<float><<<grid, 256, 0, st>>>((const float*)a, (float*)h, n8, p_drop, seed);
+    if (dtype == VER_F16) relu_dropout_fwd<__half><<<grid, 256, 0, st>>>((const __half*)a, (__half*)h, n8, p_drop, seed, ep);
+    else relu_dropout_fwd<float><<<grid, 256, 0, st>>>((const float*)a, (float*)h, n8, p_drop, seed, ep);
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;

@@ -21,33 +21,57 @@ from . import ops
 from ._lib import VER_F16, check, lib
 from .ops import _ptr, _stream
 
+# fp16 / concatenated copies of the fp32 master weights, made once per weight update instead of once per Linear
+# call.  An entry is valid while (a) every source parameter is still alive (weak references: a rebuilt model
+# cannot alias an id, and dropping the model frees the copies), (b) its autograd version counter and storage are
+# unchanged, and (c) the global generation is unchanged.  Updates that bypass the version counter (`p.data.copy_`,
+# apex / multi-tensor optimizers writing through .data, load_state_dict on some paths, manual surgery) MUST be
+# followed by invalidate_weight_cache(); optimizer steps through torch.optim and load_state_dict are hooked by
+# install_cache_hooks().  Inside a CUDA-graph capture a cache hit would freeze stale copies into the graph, so
+# graph.capture_step() invalidates first.
 _HALF_CACHE = {}
+_GENERATION = [0]
+
+
+def invalidate_weight_cache():
+    """Drop every cached low-precision weight copy (call after any weight update that does not go through
+    torch.optim / load_state_dict, e.g. writes through `.data`)."""
+    _GENERATION[0] += 1
+    _HALF_CACHE.clear()
+
+
+def install_cache_hooks(module, optimizer=None):
+    """Invalidate the copies after optimizer.step() and load_state_dict() of `module`."""
+    handles = []
+    if optimizer is not None and hasattr(optimizer, 'register_step_post_hook'):
+        handles.append(optimizer.register_step_post_hook(lambda *a, **k: invalidate_weight_cache()))
+    if hasattr(module, 'register_load_state_dict_post_hook'):
+        handles.append(module.register_load_state_dict_post_hook(lambda *a, **k: invalidate_weight_cache()))
+    return handles
+
+
+def _cached(kind, params, make):
+    import weakref
+    key = (kind,) + tuple(id(p) for p in params)
+    ver = (_GENERATION[0],) + tuple((p._version, p.data_ptr()) for p in params)
+    hit = _HALF_CACHE.get(key)
+    if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):
+        return hit[1]
+    with torch.no_grad():
+        t = make()
+    refs = tuple(weakref.ref(p, lambda _r, k=key: _HALF_CACHE.pop(k, None)) for p in params)
+    _HALF_CACHE[key] = (ver, t, refs)
+    return t
 
 
 def half_of(*params):
     """fp16 copy of a parameter (or the row-concatenation of several), refreshed when a parameter changes."""
-    key = tuple(id(p) for p in params)
-    ver = tuple((p._version, p.data_ptr()) for p in params)
-    hit = _HALF_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    with torch.no_grad():
-        t = params[0].detach().to(torch.float16) if len(params) == 1 else \
-            torch.cat([p.detach() for p in params], 0).to(torch.float16)
-    _HALF_CACHE[key] = (ver, t)
-    return t
+    return _cached('f16', params, lambda: params[0].detach().to(torch.float16) if len(params) == 1 else
+                   torch.cat([p.detach() for p in params], 0).to(torch.float16))
 
 
 def f32_cat(*params):
-    key = ('f32',) + tuple(id(p) for p in params)
-    ver = tuple((p._version, p.data_ptr()) for p in params)
-    hit = _HALF_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    with torch.no_grad():
-        t = torch.cat([p.detach().float() for p in params], 0).contiguous()
-    _HALF_CACHE[key] = (ver, t)
-    return t
+    return _cached('f32', params, lambda: torch.cat([p.detach().float() for p in params], 0).contiguous())
 
 
 # ------------------------------------------------------------------ thin kernel wrappers (no autograd)
@@ -57,7 +81,8 @@ def _ln_fwd(x, res, gamma32, beta32, p, eps, seed, save):
     z = torch.empty_like(x) if save else None
     stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if save else None
     check(lib.ver_dropout_add_layernorm_fwd(VER_F16, _ptr(x), _ptr(res), _ptr(gamma32), _ptr(beta32), _ptr(y),
-                                            _ptr(z), _ptr(stats), rows, C, float(eps), float(p), seed, _stream()))
+                                            _ptr(z), _ptr(stats), rows, C, float(eps), float(p), seed,
+                                            _ptr(ops._seed_epoch(x.device)), _stream()))
     return y, z, stats
 
 
@@ -69,7 +94,7 @@ def _ln_bwd(dy, z, stats, gamma32, p, seed):
     part = torch.empty((3, nb, C), dtype=torch.float32, device=z.device)
     check(lib.ver_dropout_add_layernorm_bwd(VER_F16, _ptr(dy), _ptr(z), _ptr(stats), _ptr(gamma32), _ptr(dx),
                                             _ptr(dres), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), rows, C,
-                                            float(p), seed, _stream()))
+                                            float(p), seed, _ptr(ops._seed_epoch(z.device)), _stream()))
     sums = part.sum(1)
     return dx, dres, sums[0], sums[1], sums[2]
 
@@ -162,7 +187,8 @@ class VoxelLayerFunction(Function):
         del proj
         # FFN: Linear -> ReLU -> Dropout -> Linear -> Dropout, + identity, LayerNorm
         h = torch.addmm(half_of(b1), y1, W116.t())
-        check(lib.ver_relu_dropout_fwd(VER_F16, _ptr(h), _ptr(h), h.numel(), float(p_ffn), seed2, _stream()))
+        check(lib.ver_relu_dropout_fwd(VER_F16, _ptr(h), _ptr(h), h.numel(), float(p_ffn), seed2,
+                                       _ptr(ops._seed_epoch(h.device)), _stream()))
         f = torch.addmm(half_of(b2), h, W216.t())
         y2, z2, st2 = _ln_fwd(f, y1, g2f, be2f, p_out, eps2, seed3, need_bwd)
         del f
@@ -207,9 +233,16 @@ class VoxelLayerFunction(Function):
         Bv, S, C = B * Ncam, Sh * Sw, NH * Dh
         gvalue = torch.empty((Bv * S, C), dtype=f32, device=q.device)
         glogits = torch.empty(logits.shape, dtype=f32, device=q.device)
+        prof = ops.PROFILE_EVENTS_BWD
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         check(lib.ver_sca_backward(VER_F16, _ptr(vimg), ops.VER_LAYOUT_TC_IMAGE, _ptr(logits), logits.shape[1],
                                    _ptr(vis.rpc), _ptr(vis.bits), _ptr(counts), _ptr(index), _ptr(dslots),
                                    _ptr(gvalue), _ptr(glogits), B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP, _stream()))
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1))
         del dslots
         # ---- logits Linear (once per voxel): dW, db, and the query gradient joins the residual branch's
         gl16, dbcat = _cast_colsum(glogits)

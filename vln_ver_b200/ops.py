@@ -13,7 +13,8 @@ from torch.autograd.function import Function, once_differentiable
 from ._lib import VER_F16, VER_F32, VerError, check, lib
 
 IMG_W, IMG_H = 1280.0, 1024.0     # hard-coded in the reference, M/voxel_encoder.py:179-180
-PROFILE_EVENTS = None             # set to a list by bench.py to collect (start, end) CUDA events
+PROFILE_EVENTS = None             # set to a list by bench.py to collect (start, end) CUDA events of the forward sampler
+PROFILE_EVENTS_BWD = None         # same for the backward sampler (fused layer / SCASampleTCFunction)
 
 
 def _ptr(t):
@@ -510,13 +511,44 @@ def add_layernorm(x, residual, gamma, beta, eps=1e-5):
     return y
 
 
+# ---- dropout keys.  key = f(torch seed, host counter) + device epoch word.  The host counter gives every dropout
+# site of every eager step its own key; the epoch word lives in device memory and is ADDED by the kernels when they
+# run, so a step captured in a CUDA graph (whose host-side keys are frozen into the graph) still draws fresh masks
+# on every replay -- the captured step calls advance_dropout_epoch() once.  Both parts are in dropout_rng_state()
+# so that a checkpoint can restore the mask sequence.
 _SEED_COUNTER = [0]
+_SEED_EPOCH = {}          # device index -> int64 tensor (1,)
 
 
 def _next_seed():
     """A fresh 64-bit Philox key per dropout site and step, derived from torch's global seed."""
     _SEED_COUNTER[0] += 1
     return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _SEED_COUNTER[0] * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+
+
+def _seed_epoch(device):
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _SEED_EPOCH.get(idx)
+    if t is None:
+        t = _SEED_EPOCH[idx] = torch.zeros(1, dtype=torch.int64, device=f'cuda:{idx}')
+    return t
+
+
+def advance_dropout_epoch(device=None):
+    """Bump the device-side epoch word (a stream-ordered in-place add: capturable).  Call once per training step
+    from inside a captured step; harmless (and unnecessary) in eager mode."""
+    _seed_epoch(device if device is not None else torch.cuda.current_device()).add_(0x632BE59BD9B4E019)
+
+
+def dropout_rng_state():
+    return {'counter': _SEED_COUNTER[0], 'epoch': {i: int(t.item()) for i, t in _SEED_EPOCH.items()}}
+
+
+def set_dropout_rng_state(state):
+    _SEED_COUNTER[0] = int(state['counter'])
+    for i, v in state.get('epoch', {}).items():
+        _seed_epoch(f'cuda:{int(i)}').fill_(int(v))
 
 
 class DropoutAddLayerNormFunction(Function):
@@ -539,7 +571,7 @@ class DropoutAddLayerNormFunction(Function):
         w32, b32 = _c(weight.detach(), torch.float32), _c(bias.detach(), torch.float32)
         check(lib.ver_dropout_add_layernorm_fwd(_code(x.dtype), _ptr(x), _ptr(r), _ptr(w32), _ptr(b32), _ptr(y),
                                                 _ptr(z), _ptr(stats), rows, C, float(eps), p_eff, seed,
-                                                _stream()))
+                                                _ptr(_seed_epoch(x.device)), _stream()))
         if need_bwd:
             ctx.save_for_backward(z, stats, w32)
             ctx.p, ctx.seed, ctx.has_res, ctx.wdtype = p_eff, seed, residual is not None, weight.dtype
@@ -559,7 +591,7 @@ class DropoutAddLayerNormFunction(Function):
         dbp = torch.empty((nb, C), dtype=torch.float32, device=z.device)
         check(lib.ver_dropout_add_layernorm_bwd(_code(z.dtype), _ptr(dy), _ptr(z), _ptr(stats), _ptr(w32),
                                                 _ptr(dx), _ptr(dres), _ptr(dgp), _ptr(dbp), None, rows, C, ctx.p,
-                                                ctx.seed, _stream()))
+                                                ctx.seed, _ptr(_seed_epoch(z.device)), _stream()))
         return dx, dres, dgp.sum(0).to(ctx.wdtype), dbp.sum(0).to(ctx.wdtype), None, None, None
 
 
@@ -575,7 +607,8 @@ class ReluDropoutFunction(Function):
         _need_cuda(a)
         assert a.is_contiguous() and a.numel() % 8 == 0
         p_eff = float(p) if training else 0.0
-        check(lib.ver_relu_dropout_fwd(_code(a.dtype), _ptr(a), _ptr(a), a.numel(), p_eff, _next_seed(), _stream()))
+        check(lib.ver_relu_dropout_fwd(_code(a.dtype), _ptr(a), _ptr(a), a.numel(), p_eff, _next_seed(),
+                                       _ptr(_seed_epoch(a.device)), _stream()))
         ctx.mark_dirty(a)
         ctx.save_for_backward(a)
         ctx.p = p_eff

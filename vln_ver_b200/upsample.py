@@ -98,11 +98,14 @@ def _weight_matrix(weight, dtype):
     cin, cout = weight.shape[:2]
     if torch.is_grad_enabled() and weight.requires_grad:
         return weight.to(dtype).permute(0, 2, 3, 4, 1).reshape(cin, 75 * cout)
+    import weakref
+    from .fused_layer import _GENERATION            # invalidate_weight_cache() drops these copies too
     key = (id(weight), dtype)
     hit = _WMAT_CACHE.get(key)
-    tag = (weight._version, weight.data_ptr(), weight.device)
-    if hit is None or hit[0] != tag:
-        hit = (tag, weight.detach().to(dtype).permute(0, 2, 3, 4, 1).reshape(cin, 75 * cout).contiguous())
+    tag = (_GENERATION[0], weight._version, weight.data_ptr(), weight.device)
+    if hit is None or hit[0] != tag or hit[2]() is not weight:
+        ref = weakref.ref(weight, lambda _r, k=key: _WMAT_CACHE.pop(k, None))
+        hit = (tag, weight.detach().to(dtype).permute(0, 2, 3, 4, 1).reshape(cin, 75 * cout).contiguous(), ref)
         _WMAT_CACHE[key] = hit
     return hit[1]
 
