@@ -546,6 +546,80 @@ def gen_head_detection():
     print('head detection ok')
 
 
+def refine_upsample_weights(i):
+    """Weights of up_sample layer i of the refine_occ fixture (133 M parameters: regenerated from a seed by the
+    generator AND by the tests instead of being stored)."""
+    g = torch.Generator().manual_seed(7000 + i)
+    w = torch.randn(768, 768, 3, 5, 5, generator=g) * 0.01
+    b = torch.randn(768, generator=g) * 0.1
+    return w, b
+
+
+def gen_head_refine():
+    """Unmodified VoxelFormerOccupancyHead.forward, default branch with refine_occ=True (HEAD:551-580): the raw
+    `.view` reinterpretations (:558, :564), the three ConvTranspose3d(768, 768) of `up_sample` (:254-258, the
+    channel count is hard-coded, so C = 768) and the column-wise occ_proj (bev_z != occ_zdim, :570-576) on a tiny
+    2 x 3 x 3 grid -> 7 x 24 x 24 occupancy cells.  Pins the oracle's refine_occ tail (it was only
+    compared with the restatement)."""
+    for mod in ('voxel_positional_embedding', 'spatial_cross_attention', 'voxel_encoder', 'voxel_decoder',
+                'voxel_transformer'):
+        mmcv_shim.import_reference('bevformer.modules.' + mod)
+    hd = mmcv_shim.import_reference('bevformer.dense_heads.voxelformer_occupancy_head')
+    mmcv_shim.register_detr_decoder_layer()
+    C, grid, seed, nq, L = 768, (2, 3, 3), 131, 4, 1
+    torch.manual_seed(seed)
+    head = hd.VoxelFormerOccupancyHead(
+        bev_h=grid[1], bev_w=grid[2], bev_z=grid[0], num_query=nq, num_classes=17, in_channels=C,
+        sync_cls_avg_factor=True, with_box_refine=True, as_two_stage=False, point_cloud_range=PC,
+        occupancy_size=[0.5, 0.5, 0.5], occ_dims=16, occupancy_classes=16, only_occ=False, only_det=False,
+        refine_occ=True,
+        transformer=mmcv_shim.ConfigDict(
+            type='VoxelPerceptionTransformer', num_cams=6, embed_dims=C, decoder_on_bev=False,
+            encoder=encoder_cfg(C, 2 * C, num_layers=1), decoder=decoder_cfg(C, L)),
+        bbox_coder=dict(type='NMSFreeCoder', pc_range=PC, max_num=50, num_classes=17),
+        positional_encoding=dict(type='VoxelLearnedPositionalEncoding', num_feats=C // 2,
+                                 row_num_embed=grid[1], col_num_embed=grid[2], z_num_embed=grid[0]),
+        loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+        loss_bbox=dict(type='L1Loss', loss_weight=0.25), loss_iou=dict(type='GIoULoss', loss_weight=0.0),
+        loss_occupancy=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)).eval()
+    assert (head.occ_xdim, head.occ_ydim, head.occ_zdim) == (24, 24, 7)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for i, conv in enumerate(head.up_sample):
+            w, b = refine_upsample_weights(i)
+            conv.weight.copy_(w)
+            conv.bias.copy_(b)
+        for n, p in head.named_parameters():
+            if n.startswith(('occ_proj', 'occ_branches')):
+                p.copy_(torch.randn(p.shape, generator=g) * (0.05 if p.dim() > 1 else 0.2))
+    Nq = grid[0] * grid[1] * grid[2]
+    bev_embed = torch.randn(Nq, 1, C, generator=g)
+    hs = torch.randn(L, nq, 1, C, generator=g)
+    init_ref = torch.rand(1, nq, 3, generator=g)
+    inter_refs = torch.rand(L, 1, nq, 3, generator=g)
+
+    class _Stub(torch.nn.Module):
+        def __init__(self, decoder):
+            super().__init__()
+            self.decoder = decoder
+
+        def forward(self, *a, **k):
+            return bev_embed, hs, init_ref, inter_refs
+    head.transformer = _Stub(head.transformer.decoder)
+    with torch.no_grad():
+        outs = head(torch.zeros(6, 1, 196, C), [dict(sample_idx='scanA_vp0')])
+    sd = dict(head.state_dict())
+    occ2 = ver_ref.occ_head(sd, '', bev_embed.permute(1, 0, 2), *grid, head.occ_xdim, head.occ_ydim, head.occ_zdim,
+                            occ_dims=16, refine_occ=True, only_occ=False)
+    err = (outs['occupancy_preds'] - occ2).abs().max().item() / outs['occupancy_preds'].abs().max().item()
+    assert err < 1e-6, err
+    out = {'bev_embed': bev_embed.numpy(), 'grid': np.array(grid), 'occ_dims3': np.array([24, 24, 7]),
+           'occupancy_preds': outs['occupancy_preds'].numpy()}
+    out.update({f'sd.{k}': v.numpy() for k, v in sd.items() if k.startswith(('occ_proj', 'occ_branches'))})
+    np.savez_compressed(os.path.join(OUT, 'head_refine_c768.npz'), **out)
+    print('head refine ok, restatement vs unmodified head', err)
+
+
 def main():
     assert mmcv_shim.reference_available(), 'needs /root/reference'
     os.makedirs(OUT, exist_ok=True)
@@ -561,6 +635,7 @@ def main():
     gen_msda3d()
     gen_decoder()
     gen_head_detection()
+    gen_head_refine()
 
 
 if __name__ == '__main__':

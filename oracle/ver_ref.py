@@ -34,6 +34,18 @@ IMG_W, IMG_H = 1280, 1024          # hard-coded at M/voxel_encoder.py:179-180
 
 
 # --------------------------------------------------------------------------- A5 / K3
+# Storage-rounding emulation (tests only).  The product's fp16-storage mode rounds activations to fp16 at fixed
+# points (value_proj output, sampler output, every GEMM output, every LayerNorm output, the view tokens and the
+# query table); the reference has no such mode.  With STORAGE_ROUND = lambda t: t.half().to(t.dtype) the functions
+# below round at the same points, which separates "storage rounding" from "arithmetic differences" when the fp16
+# product is compared with the fp64 oracle (tests/test_gpu_parity.py::test_fp16_residual_is_storage_rounding).
+STORAGE_ROUND = None
+
+
+def _r(t):
+    return t if STORAGE_ROUND is None else STORAGE_ROUND(t)
+
+
 def multi_scale_deformable_attn_pytorch(value, value_spatial_shapes,
                                         sampling_locations, attention_weights):
     """mmcv 1.4.0 `multi_scale_deformable_attn_pytorch` (2-D), restated line by
@@ -151,7 +163,7 @@ def msda3d_forward(sd, pre, query, value, reference_points, spatial_shapes,
     bs, num_query, _ = query.shape
     bs, num_value, _ = value.shape
     assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum()) == num_value
-    value = F.linear(value, sd[pre + 'value_proj.weight'], sd[pre + 'value_proj.bias'])
+    value = _r(F.linear(value, sd[pre + 'value_proj.weight'], sd[pre + 'value_proj.bias']))
     value = value.view(bs, num_value, num_heads, -1)
     sampling_offsets = F.linear(query, sd[pre + 'sampling_offsets.weight'],
                                 sd[pre + 'sampling_offsets.bias']).view(
@@ -212,8 +224,8 @@ def sca_forward_single(sd, pre, query, value, reference_points_cam, bev_mask, sp
     count = bev_mask.sum(-1) > 0
     count = count.permute(1, 2, 0).sum(-1)
     count = torch.clamp(count, min=1.0)
-    slots = slots / count[..., None]
-    slots = F.linear(slots, sd[pre + 'output_proj.weight'], sd[pre + 'output_proj.bias'])
+    slots = _r(slots / count[..., None])
+    slots = _r(F.linear(slots, sd[pre + 'output_proj.weight'], sd[pre + 'output_proj.bias']))
     return slots + inp_residual
 
 
@@ -232,8 +244,8 @@ def sca_forward(sd, pre, query, value, reference_points_cam, bev_mask, spatial_s
 def ffn_forward(sd, pre, x):
     """mmcv 1.4.0 FFN (Linear-ReLU-[Dropout]-Linear-[Dropout] + identity), eval mode;
     built at M/custom_base_transformer_layer.py:157-158 with vocc.py:134-135."""
-    h = F.relu(F.linear(x, sd[pre + 'layers.0.0.weight'], sd[pre + 'layers.0.0.bias']))
-    return x + F.linear(h, sd[pre + 'layers.1.weight'], sd[pre + 'layers.1.bias'])
+    h = _r(F.relu(F.linear(x, sd[pre + 'layers.0.0.weight'], sd[pre + 'layers.0.0.bias'])))
+    return x + _r(F.linear(h, sd[pre + 'layers.1.weight'], sd[pre + 'layers.1.bias']))
 
 
 def layer_forward(sd, pre, query, value, reference_points_cam, bev_mask, spatial_shapes,
@@ -247,8 +259,8 @@ def layer_forward(sd, pre, query, value, reference_points_cam, bev_mask, spatial
                                 reference_points_cam, bev_mask, spatial_shapes, **kw)
             attn_index += 1
         elif op == 'norm':
-            query = F.layer_norm(query, (C,), sd[f'{pre}norms.{norm_index}.weight'],
-                                 sd[f'{pre}norms.{norm_index}.bias'], 1e-5)
+            query = _r(F.layer_norm(query, (C,), sd[f'{pre}norms.{norm_index}.weight'],
+                                    sd[f'{pre}norms.{norm_index}.bias'], 1e-5))
             norm_index += 1
         elif op == 'ffn':
             query = ffn_forward(sd, f'{pre}ffns.{ffn_index}.', query)
@@ -277,12 +289,12 @@ def get_voxel_features(sd, pre, mlvl_feats, bev_queries, bev_z, bev_h, bev_w, pc
     mlvl_feats (Ncam, B, 196, C); bev_queries (Nq, C) -> (B, Nq, C)."""
     num_cam, bs, S, C = mlvl_feats.shape
     h = w = int(round(S ** 0.5))
-    bev_queries = bev_queries.unsqueeze(1).repeat(1, bs, 1)
+    bev_queries = _r(bev_queries).unsqueeze(1).repeat(1, bs, 1)
     feat = mlvl_feats.reshape(num_cam, bs, h, w, C).permute(1, 0, 4, 2, 3)
     feat = feat.flatten(3).permute(1, 0, 3, 2)
     if use_cams_embeds:
         feat = feat + sd[pre + 'cams_embeds'][:, None, None, :].to(feat.dtype)
-    feat = feat + sd[pre + 'level_embeds'][None, None, 0:1, :].to(feat.dtype)
+    feat = _r(feat + sd[pre + 'level_embeds'][None, None, 0:1, :].to(feat.dtype))
     spatial_shapes = torch.as_tensor([(h, w)], dtype=torch.long)
     feat_flatten = feat.permute(0, 2, 1, 3)                       # (Ncam, S, B, C)
     return encoder_forward(sd, pre + 'encoder.', bev_queries, feat_flatten, bev_z, bev_h, bev_w,
@@ -324,10 +336,10 @@ def occ_head_single(sd, pre, bev_embed, bev_z, bev_h, bev_w, occ_xdim, occ_ydim,
     else:
         x = bev_embed.contiguous().view(bs, bev_z, bev_h, bev_w, C)          # HEAD:334 / :566
     if bev_z == occ_zdim:
-        occ_pred = F.linear(x, sd[pre + 'occ_proj.weight'], sd[pre + 'occ_proj.bias'])
+        occ_pred = _r(F.linear(x, sd[pre + 'occ_proj.weight'], sd[pre + 'occ_proj.bias']))
     else:
         x = x.permute(0, 2, 3, 1, 4).flatten(3)
-        occ_pred = F.linear(x, sd[pre + 'occ_proj.weight'], sd[pre + 'occ_proj.bias'])
+        occ_pred = _r(F.linear(x, sd[pre + 'occ_proj.weight'], sd[pre + 'occ_proj.bias']))
         if refine_occ and not only_occ:
             occ_pred = occ_pred.view(bs, occ_xdim, occ_ydim, occ_zdim, occ_dims)
         else:
@@ -337,12 +349,12 @@ def occ_head_single(sd, pre, bev_embed, bev_z, bev_h, bev_w, occ_xdim, occ_ydim,
     occ_pred = occ_pred.reshape(bs, -1, occ_dims)
     y = occ_pred
     for i in range(num_occ_fcs):                                             # HEAD:242-248
-        y = F.linear(y, sd[f'{pre}occ_branches.{3 * i}.weight'], sd[f'{pre}occ_branches.{3 * i}.bias'])
-        y = F.layer_norm(y, (occ_dims,), sd[f'{pre}occ_branches.{3 * i + 1}.weight'],
-                         sd[f'{pre}occ_branches.{3 * i + 1}.bias'], 1e-5)
+        y = _r(F.linear(y, sd[f'{pre}occ_branches.{3 * i}.weight'], sd[f'{pre}occ_branches.{3 * i}.bias']))
+        y = _r(F.layer_norm(y, (occ_dims,), sd[f'{pre}occ_branches.{3 * i + 1}.weight'],
+                            sd[f'{pre}occ_branches.{3 * i + 1}.bias'], 1e-5))
         y = F.relu(y)
     k = 3 * num_occ_fcs
-    return F.linear(y, sd[f'{pre}occ_branches.{k}.weight'], sd[f'{pre}occ_branches.{k}.bias'])
+    return _r(F.linear(y, sd[f'{pre}occ_branches.{k}.weight'], sd[f'{pre}occ_branches.{k}.bias']))
 
 
 def occ_head(sd, pre, bev_embed_bnc, *args, only_occ=False, **kw):
@@ -450,7 +462,7 @@ def voxel_custom_msda_forward(sd, pre, query, value, reference_points, spatial_s
     bs, num_query, _ = query.shape
     _, num_value, _ = value.shape
     assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1] * spatial_shapes[:, 2]).sum()) == num_value
-    value = F.linear(value, sd[pre + 'value_proj.weight'], sd[pre + 'value_proj.bias'])
+    value = _r(F.linear(value, sd[pre + 'value_proj.weight'], sd[pre + 'value_proj.bias']))
     value = value.view(bs, num_value, num_heads, -1)
     offsets = F.linear(query, sd[pre + 'sampling_offsets.weight'], sd[pre + 'sampling_offsets.bias']).view(
         bs, num_query, num_heads, num_levels, num_points, 3)
@@ -501,8 +513,8 @@ def decoder_layer_forward(sd, pre, query, value, query_pos, reference_points, sp
                                               reference_points, spatial_shapes, query_pos=query_pos, **kw)
             attn_index += 1
         elif op == 'norm':
-            query = F.layer_norm(query, (C,), sd[f'{pre}norms.{norm_index}.weight'],
-                                 sd[f'{pre}norms.{norm_index}.bias'], 1e-5)
+            query = _r(F.layer_norm(query, (C,), sd[f'{pre}norms.{norm_index}.weight'],
+                                    sd[f'{pre}norms.{norm_index}.bias'], 1e-5))
             norm_index += 1
         elif op == 'ffn':
             query = ffn_forward(sd, f'{pre}ffns.{ffn_index}.', query)

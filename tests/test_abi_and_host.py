@@ -132,3 +132,51 @@ def test_half_cache_follows_parameter_versions():
     assert cat2 is not cat1 and torch.equal(cat2[:4], a.detach().half())
     f = F.f32_cat(a, b)
     assert f.dtype == torch.float32 and F.f32_cat(a, b) is f
+
+
+def test_weight_cache_is_invalidated_explicitly_and_by_hooks():
+    """the fp16 weight copies are keyed on the autograd version counter, which `.data` writes do
+    not bump.  Contract now: such writes must be followed by invalidate_weight_cache(); optimizer steps and
+    load_state_dict are hooked; entries die with their parameters (weak references)."""
+    import gc
+
+    import torch
+    from vln_ver_b200 import fused_layer as FL
+    FL.invalidate_weight_cache()
+    lin = torch.nn.Linear(8, 8)
+    a = FL.half_of(lin.weight)
+    assert FL.half_of(lin.weight) is a                              # cached
+    with torch.no_grad():
+        lin.weight.add_(1.0)                                        # bumps the version counter
+    b = FL.half_of(lin.weight)
+    assert b is not a and torch.equal(b, lin.weight.detach().half())
+    lin.weight.data.mul_(2.0)                                       # bypasses the version counter ...
+    assert FL.half_of(lin.weight) is b                              # ... so the copy is stale by construction
+    FL.invalidate_weight_cache()                                    # the documented remedy
+    c = FL.half_of(lin.weight)
+    assert c is not b and torch.equal(c, lin.weight.detach().half())
+    # hooks: optimizer.step() and load_state_dict() invalidate
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    FL.install_cache_hooks(lin, opt)
+    d = FL.half_of(lin.weight)
+    lin.weight.grad = torch.ones_like(lin.weight)
+    lin.bias.grad = torch.ones_like(lin.bias)
+    opt.step()
+    assert FL.half_of(lin.weight) is not d
+    e = FL.half_of(lin.weight)
+    lin.load_state_dict({k: v.clone() * 0 for k, v in lin.state_dict().items()})
+    f = FL.half_of(lin.weight)
+    assert f is not e and float(f.abs().max()) == 0.0
+    # no leak: entries go away with the module
+    n_before = len(FL._HALF_CACHE)
+    del lin, opt, a, b, c, d, e, f
+    gc.collect()
+    assert len(FL._HALF_CACHE) < max(n_before, 1)
+
+
+def test_spatial_shapes_are_read_once():
+    import torch
+    from vln_ver_b200 import ops
+    assert ops.shapes_to_host([[14, 14]]) == [[14, 14]]
+    assert ops.shapes_to_host(torch.tensor([[14, 14], [7, 7]])) == [[14, 14], [7, 7]]
+    assert ops._shapes_arg(torch.tensor([[14, 14]]))[1] == 1

@@ -106,3 +106,28 @@ def test_refine_occ_tail_shapes():
     bev = torch.randn(1, 18, C)
     y = ver_ref.occ_head(sd, '', bev, *grid, 24, 24, 7, occ_dims=16, refine_occ=True, only_occ=False)
     assert y.shape == (1, 7 * 24 * 24, 16)
+
+
+def _refine_fixture_state_dict(g):
+    """state_dict of the refine_occ fixture: the small tensors are stored, the 133 M up_sample weights are
+    regenerated from the generator's seeds (oracle/gen_golden.py::refine_upsample_weights)."""
+    from oracle.gen_golden import refine_upsample_weights
+    sd = sub(g, 'sd')
+    for i in range(3):
+        sd[f'up_sample.{i}.weight'], sd[f'up_sample.{i}.bias'] = refine_upsample_weights(i)
+    return sd
+
+
+def test_refine_occ_tail_pinned_to_the_unmodified_head():
+    """HEAD:551-580 with refine_occ=True (raw .view at :558 / :564, three ConvTranspose3d(768, 768), column
+    occ_proj): the restatement reproduces the output of the UNMODIFIED VoxelFormerOccupancyHead.forward recorded by
+    oracle/gen_golden.py::gen_head_refine (VERDICT r1: this tail was compared with the restatement only)."""
+    g = load_golden('head_refine_c768.npz')
+    sd = _refine_fixture_state_dict(g)
+    grid = g['grid'].tolist()
+    ox, oy, oz = g['occ_dims3'].tolist()
+    bev = torch.from_numpy(g['bev_embed'])                       # (Nq, 1, C) as the transformer returns it
+    with torch.no_grad():
+        y = ver_ref.occ_head(sd, '', bev.permute(1, 0, 2), *grid, ox, oy, oz, occ_dims=16, refine_occ=True,
+                             only_occ=False)
+    assert rel_err(y, torch.from_numpy(g['occupancy_preds'])) < 1e-5

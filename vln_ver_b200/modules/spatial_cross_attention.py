@@ -92,8 +92,7 @@ class SpatialCrossAttention(PrecisionMixin, BaseModule):
         da = self.deformable_attention
         hw = kwargs.get('spatial_hw')
         if hw is None:
-            hw = [int(v) for v in (spatial_shapes.tolist()[0] if isinstance(spatial_shapes, torch.Tensor)
-                                   else spatial_shapes[0])]
+            hw = [int(v) for v in ops.shapes_to_host(spatial_shapes)[0]]
         if da.num_levels != 1:
             raise NotImplementedError('fused SCA supports num_levels == 1 (vocc.py:58)')
         Sh, Sw = hw
@@ -191,7 +190,7 @@ class MSDeformableAttention3D(PrecisionMixin, BaseModule):
             value = value.permute(1, 0, 2)
         bs, num_query, _ = query.shape
         bs, num_value, _ = value.shape
-        shapes = spatial_shapes.tolist() if isinstance(spatial_shapes, torch.Tensor) else spatial_shapes
+        shapes = ops.shapes_to_host(spatial_shapes)
         assert sum(int(h) * int(w) for h, w in shapes) == num_value
 
         cd = self.compute_dtype or query.dtype

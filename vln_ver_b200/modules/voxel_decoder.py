@@ -30,7 +30,7 @@ def inverse_sigmoid(x, eps=1e-5):
 
 
 def _shape_list(spatial_shapes):
-    return spatial_shapes.tolist() if isinstance(spatial_shapes, torch.Tensor) else [list(s) for s in spatial_shapes]
+    return ops.shapes_to_host(spatial_shapes)
 
 
 # --------------------------------------------------------------------------- mmcv pieces named by vocc.py

@@ -162,7 +162,7 @@ class VoxelFormerEncoder(PrecisionMixin, TransformerLayerSequence):
             vis = self.visibility((bev_z, bev_h, bev_w), bs, kwargs.get('img_metas'), bev_query.device,
                                   num_cams=num_cams, lidar2img=kwargs.pop('lidar2img', None),
                                   originshift=kwargs.pop('originshift', None))
-        hw = spatial_shapes.tolist()[0] if isinstance(spatial_shapes, torch.Tensor) else list(spatial_shapes[0])
+        hw = ops.shapes_to_host(spatial_shapes)[0]
         bev_query = bev_query.permute(1, 0, 2)
         if bev_pos is not None:
             bev_pos = bev_pos.permute(1, 0, 2)

@@ -87,9 +87,28 @@ def visible_index(bev_mask):
 
 
 # ------------------------------------------------------------------ A5 (operator boundary)
+_SHAPES_HOST = {}
+
+
+def shapes_to_host(spatial_shapes):
+    """`spatial_shapes` as a Python list of lists.  The reference hands a (num_levels, 2|3) int64 TENSOR to every
+    layer (M/voxel_encoder.py:257-284); reading it is a device -> host synchronisation, so the value is read ONCE
+    per tensor (keyed on storage, version and shape) instead of once per layer per step."""
+    if not isinstance(spatial_shapes, torch.Tensor):
+        return [list(int(v) for v in s) for s in spatial_shapes]
+    if not spatial_shapes.is_cuda:
+        return spatial_shapes.tolist()
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape), spatial_shapes.device.index)
+    hit = _SHAPES_HOST.get(key)
+    if hit is None:
+        if len(_SHAPES_HOST) > 64:
+            _SHAPES_HOST.clear()
+        hit = _SHAPES_HOST[key] = spatial_shapes.tolist()          # the one D2H copy
+    return hit
+
+
 def _shapes_arg(spatial_shapes):
-    if isinstance(spatial_shapes, torch.Tensor):
-        spatial_shapes = spatial_shapes.tolist()          # one D2H copy if it lives on the GPU
+    spatial_shapes = shapes_to_host(spatial_shapes)
     flat = [int(v) for hw in spatial_shapes for v in hw]
     return (c_int32 * len(flat))(*flat), len(flat) // 2
 
@@ -144,8 +163,7 @@ class MultiScaleDeformableAttnFunction(Function):
     def forward(ctx, value, value_spatial_shapes, value_level_start_index,
                 sampling_locations, attention_weights, im2col_step):
         ctx.im2col_step = im2col_step
-        ctx.shapes = value_spatial_shapes.tolist() if isinstance(value_spatial_shapes, torch.Tensor) \
-            else [list(x) for x in value_spatial_shapes]
+        ctx.shapes = shapes_to_host(value_spatial_shapes)
         out = ms_deform_attn_forward(value, ctx.shapes, value_level_start_index,
                                      sampling_locations, attention_weights, im2col_step)
         ctx.save_for_backward(value, sampling_locations, attention_weights)
@@ -175,8 +193,7 @@ MultiScaleDeformableAttnFunction_fp16 = MultiScaleDeformableAttnFunction
 
 # ------------------------------------------------------------------ N2 / N3: 3-D (voxel volume) sampler
 def _shapes3_arg(spatial_shapes):
-    if isinstance(spatial_shapes, torch.Tensor):
-        spatial_shapes = spatial_shapes.tolist()
+    spatial_shapes = shapes_to_host(spatial_shapes)
     flat = [int(v) for dhw in spatial_shapes for v in dhw]
     if len(flat) % 3:
         raise VerError('3-D spatial_shapes must be (num_levels, 3) = (d, h, w)')
@@ -229,8 +246,7 @@ class VoxelMultiScaleDeformableAttnFunction(Function):
 
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, sampling_locations, attention_weights):
-        ctx.shapes = value_spatial_shapes.tolist() if isinstance(value_spatial_shapes, torch.Tensor) \
-            else [list(x) for x in value_spatial_shapes]
+        ctx.shapes = shapes_to_host(value_spatial_shapes)
         out = voxel_ms_deform_attn_forward(value, ctx.shapes, sampling_locations, attention_weights)
         ctx.save_for_backward(value, sampling_locations, attention_weights)
         return out
