@@ -195,7 +195,7 @@ def roofline_entry(kernel, ms, algorithmic, peak, peak_src, traffic_key, extra=N
 class Config:
     """model + optimizer + batches of one (mode, batch, grid) on this rank."""
 
-    def __init__(self, mode, batch, grid, dev, rank, world, local, n_pool=3):
+    def __init__(self, mode, batch, grid, dev, rank, world, local, n_pool=3, use_graph=True):
         import vln_ver_b200 as V
         from vln_ver_b200 import fused_layer
         from vln_ver_b200.ingest import pin
@@ -206,12 +206,17 @@ class Config:
         head = build_model(self.grid).to(dev)
         V.set_compute_dtype(head, torch.float16)
         self.head = self.model = head
+        self.local, self.bucket = local, None
         if self.train:
             head.train()
-            if self.ddp:
-                self.model = torch.nn.parallel.DistributedDataParallel(
-                    head, device_ids=[local], gradient_as_bucket_view=True, static_graph=True)
             self.params = [p for p in head.parameters() if p.requires_grad]
+            if self.ddp and use_graph:
+                # graphed multi-GPU step: the one exchange of SURVEY 8(e) as ONE captured NCCL all-reduce over a
+                # flat gradient buffer (torch DDP's reducer hooks cannot be carried through a capture)
+                from vln_ver_b200.dist_utils import FlatGradients
+                self.bucket = FlatGradients(self.params)
+            elif self.ddp:
+                self.wrap_ddp()
             # vocc.py:261-268; capturable: the step counter lives on the device (CUDA-graph replay)
             self.opt = torch.optim.AdamW(self.params, lr=1e-4, weight_decay=0.01, fused=True, capturable=True)
             # static scale 1024 would poison AdamW on an fp16 overflow: GradScaler skips such steps on the device
@@ -225,6 +230,15 @@ class Config:
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.pool_host[0].values())
         self.captured, self.graph_note = None, 'eager'
 
+    def wrap_ddp(self):
+        """eager multi-GPU step: torch DDP (bucketed all-reduce overlapped with backward)."""
+        if self.bucket is not None:
+            self.bucket = None
+            for p in self.params:
+                p.grad = None
+        self.model = torch.nn.parallel.DistributedDataParallel(
+            self.head, device_ids=[self.local], gradient_as_bucket_view=True, static_graph=True)
+
     # ---- one pass of the hot path over one batch; returns the loss (device scalar)
     def step(self, feats, l2i, sh, gts):
         head, model = self.head, self.model
@@ -234,8 +248,13 @@ class Config:
             return outs['occupancy_preds'].float().mean()
         outs = model(feats, None, lidar2img=l2i, originshift=sh)
         loss = head.loss_only_occupancy(None, None, None, list(gts), None, outs)['loss_occupancy']
-        self.opt.zero_grad(set_to_none=True)
+        if self.bucket is not None:
+            self.bucket.zero_()                     # gradients are views into the flat buffer: accumulate in place
+        else:
+            self.opt.zero_grad(set_to_none=True)
         self.scaler.scale(loss).backward()
+        if self.bucket is not None:
+            self.bucket.allreduce_mean_()           # the only collective of the data-parallel path
         self.scaler.unscale_(self.opt)
         torch.nn.utils.clip_grad_norm_(self.params, 300.0)                          # vocc.py:270
         self.scaler.step(self.opt)
@@ -246,11 +265,17 @@ class Config:
         from vln_ver_b200.graph import CapturedStep
         try:
             self.captured = CapturedStep(self.step, self.pool_dev[0], warmup=warmup, ddp=self.ddp and self.train)
-            self.graph_note = 'cuda graph replay'
+            self.graph_note = 'cuda graph replay' + (' (gradient all-reduce captured in the graph)'
+                                                     if self.bucket is not None else '')
         except Exception as e:  # noqa: BLE001  (fall back to eager, say why)
             self.captured = None
             self.graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+            if self.ddp and self.train:
+                self.wrap_ddp()
 
     def run(self, batch):
         return self.captured(**batch) if self.captured is not None else self.step(**batch)
@@ -367,7 +392,7 @@ def run_b200(args):
     peak, peak_src = hbm_peak()
 
     # ---------------- headline configuration (BASELINE config 2 unless overridden on the command line)
-    cfg = Config(args.mode, args.batch, args.grid, dev, rank, world, local)
+    cfg = Config(args.mode, args.batch, args.grid, dev, rank, world, local, use_graph=not args.no_graph)
     if not args.no_graph:
         cfg.capture(args.warmup)
     with ClockSampler(local) as clocks:
@@ -402,7 +427,7 @@ def run_b200(args):
             entry = {'config': name, 'workload': workload_name(mode, batch, grid)}
             try:
                 torch.cuda.reset_peak_memory_stats(dev)
-                c = Config(mode, batch, grid, dev, rank, world, local, n_pool=2)
+                c = Config(mode, batch, grid, dev, rank, world, local, n_pool=2, use_graph=not args.no_graph)
                 if not args.no_graph:
                     c.capture(2)
                 ms, _ = c.timed_device(args.sweep_steps, 2)

@@ -47,7 +47,17 @@ def _worker(rank, world, port, out):
     loss = _loss(sd, head, feats[:, lo:hi].double(), l2i[lo:hi], sh[lo:hi], gts[lo:hi])
     loss.backward()
     names = [k for k, v in sd.items() if v.grad is not None]
+    # the flat bucket of the graphed step (fp32 master gradients as views into one buffer, one collective)
+    p32 = [torch.nn.Parameter(sd[k].detach().float()) for k in names]
+    bucket = dist_utils.FlatGradients(p32)
+    bucket.zero_()
+    for p, k in zip(p32, names):
+        p.grad += sd[k].grad.float()              # accumulate into the views, as autograd does
+    bucket.allreduce_mean_()
+    flat_ok = all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in p32)
     dist_utils.allreduce_mean_([sd[k].grad for k in names])
+    for p, k in zip(p32, names):                  # same mean through both paths (fp32 vs fp64)
+        assert flat_ok and torch.allclose(p.grad.double(), sd[k].grad, rtol=1e-5, atol=1e-7), k
     ms = dist_utils.max_over_ranks(10.0 + rank)
     if rank == 0:
         torch.save({'grads': {k: sd[k].grad for k in names}, 'ms': ms}, out)
