@@ -162,11 +162,13 @@ class VoxelLayerFunction(Function):
         Wcat16 = half_of(Wso, Waw)
         bcat32 = f32_cat(bso, baw)
         # value_proj (M/spatial_cross_attention.py:336) and its tcgen05 operand image
-        v = torch.addmm(half_of(bv), feat, Wv16.t())
-        vimg = ops.value_image(v.view(Bv, S, C), NH)
-        del v
-        # sampling_offsets (+) attention_weights once per voxel (:340-343), fp32 out
-        logits = torch.addmm(bcat32, q, Wcat16.t(), out_dtype=torch.float32)
+        with ops.nvtx_range('layer.value_proj+logits'):
+            v = torch.addmm(half_of(bv), feat, Wv16.t())
+            vimg = ops.value_image(v.view(Bv, S, C), NH)
+            del v
+            # sampling_offsets (+) attention_weights once per voxel (:340-343), fp32 out
+            logits = torch.addmm(bcat32, q, Wcat16.t(), out_dtype=torch.float32)
+        ops.nvtx_push('layer.sampler_fwd')
         slots = torch.empty((B * Nq, C), dtype=torch.float16, device=q.device)
         order, smask, tile_union = vis.order
         prof = ops.PROFILE_EVENTS
@@ -179,19 +181,24 @@ class VoxelLayerFunction(Function):
         if prof is not None:
             e1.record()
             prof.append((e0, e1))
+        ops.nvtx_pop()
         # output_proj, dropout + residual + LayerNorm (:174-176, 'norm')
+        ops.nvtx_push('layer.output_proj+norm')
         proj = torch.addmm(half_of(bo), slots, Wo16.t())
         seed1, seed2, seed3 = ops._next_seed(), ops._next_seed(), ops._next_seed()
         g1f, be1f, g2f, be2f = (t.detach().float().contiguous() for t in (g1, be1, g2, be2))
         y1, z1, st1 = _ln_fwd(proj, q, g1f, be1f, p_attn, eps1, seed1, need_bwd)
         del proj
+        ops.nvtx_pop()
         # FFN: Linear -> ReLU -> Dropout -> Linear -> Dropout, + identity, LayerNorm
+        ops.nvtx_push('layer.ffn+norm')
         h = torch.addmm(half_of(b1), y1, W116.t())
         check(lib.ver_relu_dropout_fwd(VER_F16, _ptr(h), _ptr(h), h.numel(), float(p_ffn), seed2,
                                        _ptr(ops._seed_epoch(h.device)), _stream()))
         f = torch.addmm(half_of(b2), h, W216.t())
         y2, z2, st2 = _ln_fwd(f, y1, g2f, be2f, p_out, eps2, seed3, need_bwd)
         del f
+        ops.nvtx_pop()
         if need_bwd:
             ctx.save_for_backward(q, feat, vimg, logits, slots, z1, st1, y1, h, z2, st2, Wv16, Wcat16, Wo16, W116,
                                   W216, g1f, g2f)
@@ -214,6 +221,7 @@ class VoxelLayerFunction(Function):
         if dy2.dtype != torch.float16:
             dy2 = dy2.to(torch.float16)
         # ---- norm 2 / FFN
+        ops.nvtx_push('layer.bwd.ffn+norm')
         df, dy1, dg2, dbe2, db2 = _ln_bwd(dy2, z2, st2, g2f, p_out, seed3)
         dW2 = torch.mm(df.t(), h, out_dtype=f32)
         dh = torch.mm(df, W216)
@@ -222,13 +230,17 @@ class VoxelLayerFunction(Function):
         dW1 = torch.mm(dh.t(), y1, out_dtype=f32)
         dy1.addmm_(dh, W116)                                # + residual branch, accumulated by the GEMM
         del dh
+        ops.nvtx_pop()
         # ---- norm 1 / output_proj
+        ops.nvtx_push('layer.bwd.output_proj+norm')
         dproj, dq, dg1, dbe1, dbo = _ln_bwd(dy1, z1, st1, g1f, p_attn, seed1)
         del dy1
         dWo = torch.mm(dproj.t(), slots, out_dtype=f32)
         dslots = torch.mm(dproj, Wo16)
         del dproj
+        ops.nvtx_pop()
         # ---- fused sampler backward (A5 backward + SCA scatter)
+        ops.nvtx_push('layer.bwd.sampler')
         counts, index = vis.index
         Bv, S, C = B * Ncam, Sh * Sw, NH * Dh
         gvalue = torch.empty((Bv * S, C), dtype=f32, device=q.device)
@@ -244,7 +256,9 @@ class VoxelLayerFunction(Function):
             e1.record()
             prof.append((e0, e1))
         del dslots
+        ops.nvtx_pop()
         # ---- logits Linear (once per voxel): dW, db, and the query gradient joins the residual branch's
+        ops.nvtx_push('layer.bwd.logits+value_proj')
         gl16, dbcat = _cast_colsum(glogits)
         del glogits
         dWcat = torch.mm(gl16.t(), q, out_dtype=f32)
@@ -255,6 +269,7 @@ class VoxelLayerFunction(Function):
         del gvalue
         dWv = torch.mm(gv16.t(), feat, out_dtype=f32)
         dfeat = torch.mm(gv16, Wv16) if ctx.needs_input_grad[1] else None
+        ops.nvtx_pop()
         n_so = ctx.n_so
         grads = [dWv, dbv, dWcat[:n_so], dbcat[:n_so], dWcat[n_so:], dbcat[n_so:], dWo, dbo, dg1, dbe1, dW1, db1,
                  dW2, db2, dg2, dbe2]

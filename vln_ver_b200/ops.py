@@ -5,6 +5,7 @@ bookkeeping.  Every function requires CUDA tensors and raises otherwise -- there
 no CPU or eager fallback (the CPU restatement lives in oracle/ and is test-only).
 """
 import ctypes
+import os
 from ctypes import c_double, c_int32, c_void_p
 
 import torch
@@ -15,6 +16,33 @@ from ._lib import VER_F16, VER_F32, VerError, check, lib
 IMG_W, IMG_H = 1280.0, 1024.0     # hard-coded in the reference, M/voxel_encoder.py:179-180
 PROFILE_EVENTS = None             # set to a list by bench.py to collect (start, end) CUDA events of the forward sampler
 PROFILE_EVENTS_BWD = None         # same for the backward sampler (fused layer / SCASampleTCFunction)
+
+
+class nvtx_range:
+    """NVTX range around a phase of the path (SURVEY section 5 tracing row) -- visible in nsys / ncu timelines.
+    Off unless VER_NVTX=1: the markers are host calls on the launch path."""
+    ON = os.environ.get('VER_NVTX', '0') == '1'
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_range.ON:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if nvtx_range.ON:
+            torch.cuda.nvtx.range_pop()
+
+
+def nvtx_push(name):
+    if nvtx_range.ON:
+        torch.cuda.nvtx.range_push(name)
+
+
+def nvtx_pop():
+    if nvtx_range.ON:
+        torch.cuda.nvtx.range_pop()
 
 
 def _ptr(t):
