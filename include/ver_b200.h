@@ -235,6 +235,22 @@ int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const void* z, cons
                                   const float* gamma, void* dx, void* dresidual, float* dgamma_part,
                                   float* dbeta_part, float* dxsum_part, int64_t rows, int C, float p_drop,
                                   uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream);
+/* ---------------------------------------------------------------- K5: the dense projections
+ * nn.Linear as a hand-written tcgen05 GEMM with a fused epilogue (csrc/gemm_tc.cu):
+ *     out[M, N] = epilogue(a[M, K] @ w[N, K]^T + bias[N])
+ * for value_proj (M/spatial_cross_attention.py:336), sampling_offsets (+) attention_weights (:340-343),
+ * output_proj (:174) and the two FFN Linears (M/custom_base_transformer_layer.py:157-158, vocc.py:134-135).
+ *   epilogue   0: bias -> fp16;  1: bias -> fp32 (the offset / weight logits);
+ *              2: bias + ReLU + dropout(p_drop) -> fp16 (= ver_relu_dropout_fwd applied to the Linear's output,
+ *                 same Philox mask for the same seed / seed_epoch: element index = row * N + column)
+ *   a, w       fp16 row-major, leading dimensions lda / ldw (elements, multiples of 8), 16-byte aligned
+ *   bias       fp32 [N] or NULL;   out: fp16 / fp32 row-major, leading dimension ldo
+ *   requires   K % 64 == 0 and N % 128 == 0 or N % 192 == 0 (ver_linear_supported); any M
+ * fp32 accumulation in tensor memory; one persistent CTA per SM. */
+int ver_linear_supported(int M, int N, int K);
+int ver_linear_f16(int epilogue, const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldo,
+                   int M, int N, int K, float p_drop, uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream);
+
 /* FFN inner activation (mmcv FFN: Linear -> ReLU -> Dropout): h = dropout(relu(a)), in place allowed;
  * backward da = dh * [h > 0] / (1 - p).  n % 8 == 0.
  * Column sums (bias gradients) come as partial sums: colsum_part is [ver_colsum_partial_rows(), 8] fp32 and row t
@@ -249,6 +265,14 @@ int ver_relu_dropout_bwd(int dtype, const void* dh, const void* h, void* da, int
  * gradients of the sampler's backward into GEMM operands + bias gradients in one pass. */
 int ver_cast_colsum(int dtype, const float* x, void* y, int64_t rows, int C, float* colsum_part,
                     ver_stream_t stream);
+/* out[C] = sum over the P rows of part[P, C] (fp32): folds the partial sums above (view the per-thread 8-float groups
+ * as rows of C floats) in one deterministic two-level launch.  scratch: ver_colsum_fold_scratch_floats(C) floats whose
+ * LAST word is a counter that must be zero on entry (the kernel leaves it zero); one launch per scratch at a time. */
+int ver_colsum_fold_scratch_floats(int C);
+int ver_colsum_fold(const float* part, int64_t P, int C, float* out, float* scratch, ver_stream_t stream);
+/* Column sums of an fp16 matrix x[rows, C] as partial sums (layout as above): the bias gradient of a Linear whose
+ * output gradient is already fp16 (the occupancy head's occ_proj / occ_branches, HEAD:236-248). */
+int ver_colsum_f16(const void* x, int64_t rows, int C, float* colsum_part, ver_stream_t stream);
 
 /* ---------------------------------------------------------------- A11
  * Sigmoid focal loss of mmdet FocalLoss(use_sigmoid=True) (vocc.py:190-195; calls HEAD:981,

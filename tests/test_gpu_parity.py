@@ -907,3 +907,36 @@ def test_device_prefetcher_copies_each_batch_once_in_order():
     assert seen == 5
     assert pf.h2d_bytes == sum(t.numel() * t.element_size() for b in host for t in b.values())
     assert list(DevicePrefetcher(iter([]), 'cuda')) == []
+
+
+# ------------------------------------------------------------------ K5: tcgen05 Linear with fused epilogues
+@pytest.mark.parametrize('M,N,K,epi,p', [(256, 256, 64, 0, 0.0), (1000, 256, 128, 0, 0.0), (300, 128, 192, 0, 0.0),
+                                         (4096, 192, 768, 1, 0.0), (5000, 768, 768, 0, 0.0), (333, 384, 64, 1, 0.0),
+                                         (3000, 1536, 768, 2, 0.0), (3000, 1536, 768, 2, 0.1), (2500, 768, 1536, 0, 0.0)])
+def test_linear_tc_vs_fp32_reference(M, N, K, epi, p):
+    """ver_linear_f16 (csrc/gemm_tc.cu) = nn.Linear (+ ReLU + dropout) as the reference applies it
+    (M/spatial_cross_attention.py:174,336,340-343; mmcv FFN): fp32 reference on the fp16-rounded operands, ragged M
+    (rows past M never written), every epilogue; the dropout mask is ver_relu_dropout_fwd's for the same seed."""
+    from vln_ver_b200._lib import VER_F16, check as lcheck, lib as _l
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = (torch.randn(M, K, device=DEV, generator=g) * 0.5).half()
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).half()
+    b = torch.randn(N, device=DEV, generator=g)
+    out = ops.linear_tc(x, w, b, epilogue=epi, p=p, seed=99)
+    assert out.dtype == (torch.float32 if epi == ops.LINEAR_BIAS_F32 else torch.float16) and out.shape == (M, N)
+    ref = x.float() @ w.float().t() + b
+    if epi == ops.LINEAR_BIAS_RELU_DROPOUT_F16:
+        ref = torch.relu(ref)
+        if p > 0:
+            h = ops.linear_tc(x, w, b, epilogue=ops.LINEAR_BIAS_F16)
+            lcheck(_l.ver_relu_dropout_fwd(VER_F16, h.data_ptr(), h.data_ptr(), h.numel(), p, 99,
+                                           ops._seed_epoch(h.device).data_ptr(), torch.cuda.current_stream().cuda_stream))
+            keep = h != 0
+            pos = ref.half() > 0
+            assert abs(1.0 - keep[pos].float().mean().item() - p) < 0.02
+            ref = torch.where(keep, ref / (1 - p), torch.zeros_like(ref))
+            # identical mask: the fused epilogue zeroes exactly the elements the standalone kernel zeroes
+            assert torch.equal(out != 0, keep | ((out != 0) & ~pos))
+    assert rel_err(out, ref) < (1e-5 if epi == ops.LINEAR_BIAS_F32 else 1e-3)
+    with pytest.raises(ops.VerError):
+        ops.linear_tc(x[:, :K - 8].contiguous(), w[:, :K - 8].contiguous(), b)      # K % 64 != 0

@@ -62,9 +62,15 @@ def _load():
         'ver_dropout_add_layernorm_bwd': (c_int, [c_int, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_float,
                                                   ctypes.c_uint64, P, P]),
         'ver_relu_dropout_fwd': (c_int, [c_int, P, P, c_int64, c_float, ctypes.c_uint64, P, P]),
+        'ver_linear_supported': (c_int, [c_int, c_int, c_int]),
+        'ver_linear_f16': (c_int, [c_int, P, c_int, P, c_int, P, P, c_int, c_int, c_int, c_int, c_float,
+                                   ctypes.c_uint64, P, P]),
         'ver_colsum_partial_rows': (c_int, []),
         'ver_relu_dropout_bwd': (c_int, [c_int, P, P, P, c_int64, c_float, c_int, P, P]),
         'ver_cast_colsum': (c_int, [c_int, P, P, c_int64, c_int, P, P]),
+        'ver_colsum_f16': (c_int, [P, c_int64, c_int, P, P]),
+        'ver_colsum_fold_scratch_floats': (c_int, [c_int]),
+        'ver_colsum_fold': (c_int, [P, c_int64, c_int, P, P, P]),
         'ver_focal_loss': (c_int, [P, P, c_int, P, P, P, P, c_int64, c_int, c_float, c_float, P]),
         'ver_occupancy_decode': (c_int, [P, c_int64, c_int, c_float, P, P, P, P]),
     }

@@ -6,41 +6,9 @@
 //   z = residual + dropout(x) ; y = LayerNorm(z) * gamma + beta          (SCA / FFN -> 'norm')
 //   h = dropout(relu(a))                                                  (FFN inner activation)
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
-
-// ---------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t seed) {
-    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0;
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
-// keep-mask for 8 consecutive elements starting at flat element index e0 (e0 % 8 == 0):
-// one Philox call yields 128 random bits = 8 x 16-bit uniforms
-__device__ __forceinline__ uint32_t keep8(uint64_t e0, uint64_t seed, uint32_t thr16) {
-    const uint4 r = philox4x32(e0 >> 3, seed);
-    uint32_t m = 0;
-    m |= ((r.x & 0xffff) >= thr16) << 0;
-    m |= ((r.x >> 16) >= thr16) << 1;
-    m |= ((r.y & 0xffff) >= thr16) << 2;
-    m |= ((r.y >> 16) >= thr16) << 3;
-    m |= ((r.z & 0xffff) >= thr16) << 4;
-    m |= ((r.z >> 16) >= thr16) << 5;
-    m |= ((r.w & 0xffff) >= thr16) << 6;
-    m |= ((r.w >> 16) >= thr16) << 7;
-    return m;
-}
 
 template <typename T>
 struct Vec8;
@@ -391,6 +359,25 @@ cast_colsum_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n8, f
     o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
+// column sums of an fp16 matrix (bias gradient of a Linear whose output gradient is already fp16)
+__global__ void __launch_bounds__(256)
+colsum_f16_kernel(const __half* __restrict__ x, int64_t n8, float* __restrict__ part) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec8<__half> v;
+        float f[8];
+        v.load(x + i * 8);
+        v.get(f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    float4* o = reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
 constexpr int kColsumGrid = 148 * 12;      // x 256 threads: a multiple of 3 * 256, i.e. of C / 8 for C | 6144
 
 int ln_grid(int64_t rows) {
@@ -494,6 +481,66 @@ extern "C" int ver_relu_dropout_bwd(int dtype, const void* dh, const void* h, vo
     }
     if (dtype == VER_F16) relu_dropout_bwd<__half><<<grid, 256, 0, st>>>((const __half*)dh, (const __half*)h, (__half*)da, n8, p_drop, colsum_part);
     else relu_dropout_bwd<float><<<grid, 256, 0, st>>>((const float*)dh, (const float*)h, (float*)da, n8, p_drop, colsum_part);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+// ---------------------------------------------------------------- out[C] = sum over the P rows of part[P, C]
+// Folds the partial sums the kernels above emit (per-thread 8-float groups viewed as rows of C floats, or per-block
+// rows).  Two levels in one launch, deterministic: every block reduces its slice of rows into block_part[b][C], the
+// block that finishes last (threadfence + counter) adds the block partials in a fixed order.  Replaces a torch
+// reduction that took 30 us per call (57 calls per training step) because its output has only C elements.
+constexpr int kFoldBlocks = 296;
+__global__ void __launch_bounds__(256)
+colsum_fold_kernel(const float* __restrict__ part, int64_t P, int C, float* __restrict__ out,
+                   float* __restrict__ block_part, unsigned int* __restrict__ counter) {
+    const int nb = gridDim.x;
+    const int64_t per = (P + nb - 1) / nb, r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < P ? r0 + per : P;
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t r = r0; r < r1; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(part + r * C + c);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<float4*>(block_part + (size_t)blockIdx.x * C + c) = a;
+    }
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == (unsigned int)nb - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < nb; ++b) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(block_part + (size_t)b * C + c));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + c) = a;
+    }
+    if (threadIdx.x == 0) *counter = 0;           // ready for the next launch on this stream
+}
+
+extern "C" int ver_colsum_fold_scratch_floats(int C) { return kFoldBlocks * C + 4; }
+
+extern "C" int ver_colsum_fold(const float* part, int64_t P, int C, float* out, float* scratch, ver_stream_t stream) {
+    VER_CHECK_ARG(part && out && scratch && P > 0 && C > 0 && C % 4 == 0, "bad arguments");
+    // scratch: [kFoldBlocks * C] block partials + one counter word that must be ZERO on entry (the kernel resets it)
+    const int nb = (int)(P < kFoldBlocks ? P : kFoldBlocks);
+    colsum_fold_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(part, P, C, out, scratch,
+                                                             reinterpret_cast<unsigned int*>(scratch + (size_t)kFoldBlocks * C));
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+extern "C" int ver_colsum_f16(const void* x, int64_t rows, int C, float* colsum_part, ver_stream_t stream) {
+    VER_CHECK_ARG(x && colsum_part && rows > 0, "bad arguments");
+    VER_CHECK_ARG(C > 0 && C % 8 == 0 && ((int64_t)kColsumGrid * 256) % (C / 8) == 0,
+                  "column sums need C / 8 to divide %d (got C = %d)", kColsumGrid * 256, C);
+    colsum_f16_kernel<<<kColsumGrid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, rows * C / 8, colsum_part);
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;

@@ -32,6 +32,13 @@ from .ops import _ptr, _stream
 _HALF_CACHE = {}
 _GENERATION = [0]
 
+# Which Linear layers of the layer's FORWARD run on the hand-written tcgen05 GEMM (csrc/gemm_tc.cu) instead of the
+# library GEMM.  Measured on B200 at the benchmark shape (profiles/r02f_gemm_check.txt): the offset / weight logits
+# (N = 192, fp32 out) 95 us against 194 us, FFN1 with bias + ReLU + dropout fused 492 us against 644 us for library
+# GEMM + ver_relu_dropout_fwd; the three plain N = 768 projections are still 0.78-0.86x of the library (a single-CTA
+# 128 x 256 tile is shared-memory-bandwidth bound at ~70 % of the tensor peak), so they stay on the library.
+TC_GEMM = {'logits': True, 'ffn1': True, 'value_proj': False, 'output_proj': False, 'ffn2': False}
+
 
 def invalidate_weight_cache():
     """Drop every cached low-precision weight copy (call after any weight update that does not go through
@@ -95,16 +102,32 @@ def _ln_bwd(dy, z, stats, gamma32, p, seed):
     check(lib.ver_dropout_add_layernorm_bwd(VER_F16, _ptr(dy), _ptr(z), _ptr(stats), _ptr(gamma32), _ptr(dx),
                                             _ptr(dres), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), rows, C,
                                             float(p), seed, _ptr(ops._seed_epoch(z.device)), _stream()))
-    sums = part.sum(1)
-    return dx, dres, sums[0], sums[1], sums[2]
+    return dx, dres, _fold_rows(part[0]), _fold_rows(part[1]), _fold_rows(part[2])
 
 
 def _colsum_part(device):
     return torch.empty((lib.ver_colsum_partial_rows(), 8), dtype=torch.float32, device=device)
 
 
+_FOLD_SCRATCH = {}
+
+
+def _fold_rows(part2d):
+    """(P, C) fp32 partial sums -> (C,): ver_colsum_fold (one deterministic two-level launch)."""
+    P, C = part2d.shape
+    key = (part2d.device.index, C)
+    scratch = _FOLD_SCRATCH.get(key)
+    if scratch is None:      # zeroed once: the kernel leaves the counter word zero
+        scratch = _FOLD_SCRATCH[key] = torch.zeros(lib.ver_colsum_fold_scratch_floats(C), dtype=torch.float32,
+                                                   device=part2d.device)
+    out = torch.empty(C, dtype=torch.float32, device=part2d.device)
+    check(lib.ver_colsum_fold(_ptr(part2d), P, C, _ptr(out), _ptr(scratch), _stream()))
+    return out
+
+
 def _fold(part, C):
-    return part.view(-1, C // 8, 8).sum(0).view(C)
+    """per-thread partials (n_threads, 8), thread t holding column group t % (C / 8) -> (C,)"""
+    return _fold_rows(part.view(-1, C))
 
 
 def _relu_dropout_bwd_(dh, h, p):
@@ -122,6 +145,54 @@ def _cast_colsum(x32):
     part = _colsum_part(x32.device)
     check(lib.ver_cast_colsum(VER_F16, _ptr(x32), _ptr(y), rows, C, _ptr(part), _stream()))
     return y, _fold(part, C)
+
+
+class LinearF16Function(Function):
+    """y = x @ W^T + b with fp16 storage for the occupancy head's Linear layers (HEAD:236-248): cached fp16 weight
+    copies, and a hand-written backward whose bias gradient is a column-sum kernel over the fp16 output gradient
+    (torch's fp16 sum reduction took 0.13 ms per Linear at 204 800 rows, 0.58 ms per step) and whose weight gradient
+    is written straight in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        """x (rows, K) -> (rows, N): 2-D in, 2-D out (a view made inside a Function may not be modified in place by
+        the caller; the FFN's ReLU is in place)."""
+        w16 = half_of(weight)
+        b16 = half_of(bias) if bias is not None else None
+        x2 = x if x.dtype == torch.float16 else x.to(torch.float16)
+        x2 = x2.contiguous()
+        y = torch.addmm(b16, x2, w16.t()) if b16 is not None else torch.mm(x2, w16.t())
+        ctx.save_for_backward(x2, w16)
+        ctx.meta = (x.shape, x.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, w16 = ctx.saved_tensors
+        xshape, xdtype, wdtype, bdtype = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if dy2.dtype != torch.float16:
+            dy2 = dy2.to(torch.float16)
+        dy2 = dy2.contiguous()
+        N = dy2.shape[1]
+        dx = torch.mm(dy2, w16).view(xshape).to(xdtype) if ctx.needs_input_grad[0] else None
+        dw = torch.mm(dy2.t(), x2, out_dtype=torch.float32).to(wdtype) if ctx.needs_input_grad[1] else None
+        db = None
+        if bdtype is not None and ctx.needs_input_grad[2]:
+            n_part = lib.ver_colsum_partial_rows()
+            if N % 8 == 0 and n_part % (N // 8) == 0:
+                part = _colsum_part(dy2.device)
+                check(lib.ver_colsum_f16(_ptr(dy2), dy2.shape[0], N, _ptr(part), _stream()))
+                db = _fold(part, N).to(bdtype)
+            else:
+                db = dy2.float().sum(0).to(bdtype)
+        return dx, dw, db
+
+
+def linear_f16(x, layer):
+    y = LinearF16Function.apply(x.reshape(-1, x.shape[-1]), layer.weight, layer.bias)
+    return y.view(*x.shape[:-1], layer.weight.shape[0])
 
 
 def supported(q, feat, vis, NH, NP, S, F):
@@ -163,11 +234,17 @@ class VoxelLayerFunction(Function):
         bcat32 = f32_cat(bso, baw)
         # value_proj (M/spatial_cross_attention.py:336) and its tcgen05 operand image
         with ops.nvtx_range('layer.value_proj+logits'):
-            v = torch.addmm(half_of(bv), feat, Wv16.t())
+            if TC_GEMM['value_proj'] and ops.linear_tc_supported(feat, Wv16):
+                v = ops.linear_tc(feat, Wv16, bv, ops.LINEAR_BIAS_F16)
+            else:
+                v = torch.addmm(half_of(bv), feat, Wv16.t())
             vimg = ops.value_image(v.view(Bv, S, C), NH)
             del v
             # sampling_offsets (+) attention_weights once per voxel (:340-343), fp32 out
-            logits = torch.addmm(bcat32, q, Wcat16.t(), out_dtype=torch.float32)
+            if TC_GEMM['logits'] and ops.linear_tc_supported(q, Wcat16):
+                logits = ops.linear_tc(q, Wcat16, bcat32, ops.LINEAR_BIAS_F32)
+            else:
+                logits = torch.addmm(bcat32, q, Wcat16.t(), out_dtype=torch.float32)
         ops.nvtx_push('layer.sampler_fwd')
         slots = torch.empty((B * Nq, C), dtype=torch.float16, device=q.device)
         order, smask, tile_union = vis.order
@@ -184,7 +261,10 @@ class VoxelLayerFunction(Function):
         ops.nvtx_pop()
         # output_proj, dropout + residual + LayerNorm (:174-176, 'norm')
         ops.nvtx_push('layer.output_proj+norm')
-        proj = torch.addmm(half_of(bo), slots, Wo16.t())
+        if TC_GEMM['output_proj'] and ops.linear_tc_supported(slots, Wo16):
+            proj = ops.linear_tc(slots, Wo16, bo, ops.LINEAR_BIAS_F16)
+        else:
+            proj = torch.addmm(half_of(bo), slots, Wo16.t())
         seed1, seed2, seed3 = ops._next_seed(), ops._next_seed(), ops._next_seed()
         g1f, be1f, g2f, be2f = (t.detach().float().contiguous() for t in (g1, be1, g2, be2))
         y1, z1, st1 = _ln_fwd(proj, q, g1f, be1f, p_attn, eps1, seed1, need_bwd)
@@ -192,10 +272,17 @@ class VoxelLayerFunction(Function):
         ops.nvtx_pop()
         # FFN: Linear -> ReLU -> Dropout -> Linear -> Dropout, + identity, LayerNorm
         ops.nvtx_push('layer.ffn+norm')
-        h = torch.addmm(half_of(b1), y1, W116.t())
-        check(lib.ver_relu_dropout_fwd(VER_F16, _ptr(h), _ptr(h), h.numel(), float(p_ffn), seed2,
-                                       _ptr(ops._seed_epoch(h.device)), _stream()))
-        f = torch.addmm(half_of(b2), h, W216.t())
+        if TC_GEMM['ffn1'] and ops.linear_tc_supported(y1, W116):
+            # Linear + bias + ReLU + dropout in the GEMM epilogue: no separate pass over the (rows, 1536) tensor
+            h = ops.linear_tc(y1, W116, b1, ops.LINEAR_BIAS_RELU_DROPOUT_F16, p=float(p_ffn), seed=seed2)
+        else:
+            h = torch.addmm(half_of(b1), y1, W116.t())
+            check(lib.ver_relu_dropout_fwd(VER_F16, _ptr(h), _ptr(h), h.numel(), float(p_ffn), seed2,
+                                           _ptr(ops._seed_epoch(h.device)), _stream()))
+        if TC_GEMM['ffn2'] and ops.linear_tc_supported(h, W216):
+            f = ops.linear_tc(h, W216, b2, ops.LINEAR_BIAS_F16)
+        else:
+            f = torch.addmm(half_of(b2), h, W216.t())
         y2, z2, st2 = _ln_fwd(f, y1, g2f, be2f, p_out, eps2, seed3, need_bwd)
         del f
         ops.nvtx_pop()

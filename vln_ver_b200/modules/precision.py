@@ -16,6 +16,11 @@ class PrecisionMixin:
     @staticmethod
     def _linear(x, layer, cd):
         w, b = layer.weight, layer.bias
+        if (cd == torch.float16 and x.is_cuda and torch.is_grad_enabled()
+                and (w.requires_grad or x.requires_grad) and w.dtype == torch.float32):
+            # fp16-storage training: cached fp16 weights + hand-written backward (bias gradient by column-sum kernel)
+            from ..fused_layer import linear_f16
+            return linear_f16(x, layer)
         if x.dtype != cd:
             x = x.to(cd)
         if w.dtype != cd:

@@ -673,6 +673,31 @@ def relu_dropout_(a, p=0.0, training=False):
     return ReluDropoutFunction.apply(a, p, training)
 
 
+# ------------------------------------------------------------------ K5: tcgen05 Linear with fused epilogue
+LINEAR_BIAS_F16, LINEAR_BIAS_F32, LINEAR_BIAS_RELU_DROPOUT_F16 = 0, 1, 2
+
+
+def linear_tc_supported(x, weight):
+    return (x.is_cuda and x.dtype == torch.float16 and weight.dtype == torch.float16 and x.dim() == 2
+            and bool(lib.ver_linear_supported(x.shape[0], weight.shape[0], x.shape[1])))
+
+
+def linear_tc(x, weight, bias=None, epilogue=LINEAR_BIAS_F16, p=0.0, seed=0):
+    """out = epilogue(x @ weight^T + bias) on the hand-written tcgen05 GEMM (csrc/gemm_tc.cu; no autograd).
+    x (M, K) fp16, weight (N, K) fp16 (nn.Linear layout), bias (N,) fp32 or None."""
+    _need_cuda(x, weight)
+    assert x.dtype == torch.float16 and weight.dtype == torch.float16 and x.dim() == 2 and weight.dim() == 2
+    x, weight = _c(x), _c(weight)
+    M, K = x.shape
+    N = weight.shape[0]
+    assert weight.shape[1] == K
+    b32 = _c(bias.detach(), torch.float32) if bias is not None else None
+    out = torch.empty((M, N), dtype=torch.float32 if epilogue == LINEAR_BIAS_F32 else torch.float16, device=x.device)
+    check(lib.ver_linear_f16(int(epilogue), _ptr(x), K, _ptr(weight), K, _ptr(b32), _ptr(out), N, M, N, K, float(p),
+                             int(seed), _ptr(_seed_epoch(x.device)) if p > 0 else None, _stream()))
+    return out
+
+
 # ------------------------------------------------------------------ A11, A12
 class _FocalFunction(Function):
     @staticmethod
