@@ -255,3 +255,11 @@ def test_head_default_forward_with_decoder_vs_oracle():
     assert rel_err(outs['all_bbox_preds'], box_r) < 1e-5
     assert rel_err(outs['occupancy_preds'], occ_r) < 1e-5
     assert outs['all_layout_preds'] is None
+    # default-branch loss(): the occupancy term of the last decoder layer (HEAD:1324-1332, :977-986)
+    gts = [torch.from_numpy(x) for x in synth.make_occ_gt(B, head.voxel_num, frac=0.2, seed=77)]
+    loss_ref = ver_ref.occupancy_loss(occ_r, gts)
+    losses = head.loss(None, None, None, [cuda(t) for t in gts], None, outs)
+    assert set(losses) == {'loss_occupancy', 'loss_flow'} and float(losses['loss_flow']) == 0.0
+    assert abs(losses['loss_occupancy'].item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+    with pytest.raises(NotImplementedError):
+        head.loss(None, None, None, None, None, dict(outs, occupancy_preds=None))

@@ -80,7 +80,18 @@ def bench(M, N, K, epi, name):
 
 
 def main():
+    _lib.lib.ver_debug_gemm_variant.argtypes = [__import__('ctypes').c_int]
     ok = True
+    # two-CTA kernel (N % 256 == 0, fp16 out) first: ragged M incl. a fully out-of-range second half
+    _lib.lib.ver_debug_gemm_variant(2)
+    for M, N, K, epi, p in ((256, 256, 64, 0, 0.0), (300, 256, 128, 0, 0.0), (5000, 768, 768, 0, 0.0),
+                            (3000, 1536, 768, 2, 0.1), (2500, 768, 1536, 0, 0.0), (28224, 768, 768, 0, 0.0)):
+        ok = check(M, N, K, epi, p) and ok
+        if not ok:
+            print('two-CTA kernel FAILED', flush=True)
+            sys.exit(1)
+    print('two-CTA kernel OK', flush=True)
+    _lib.lib.ver_debug_gemm_variant(1)
     for M, N, K, epi, p in ((256, 256, 64, 0, 0.0), (1000, 256, 128, 0, 0.0), (300, 128, 192, 0, 0.0),
                             (4096, 192, 768, 1, 0.0), (5000, 768, 768, 0, 0.0), (3000, 1536, 768, 2, 0.0),
                             (3000, 1536, 768, 2, 0.1), (2500, 768, 1536, 0, 0.0)):
@@ -91,6 +102,16 @@ def main():
     if not ok:
         sys.exit(1)
     rows = 8 * 25600
+    for variant, tag in ((2, 'two-CTA'), (1, 'one-CTA')):
+        _lib.lib.ver_debug_gemm_variant(variant)
+        print(f'--- tcgen05 column = {tag} kernel where it applies', flush=True)
+        bench(8 * 18 * 196, 768, 768, 0, 'value_proj')
+        bench(rows, 768, 768, 0, 'output_proj')
+        bench(rows, 1536, 768, 2, 'FFN1 + ReLU + dropout')
+        bench(rows, 768, 1536, 0, 'FFN2')
+    _lib.lib.ver_debug_gemm_variant(0)
+    bench(rows, 192, 768, 1, 'offsets+weights logits')
+    return
     bench(8 * 18 * 196, 768, 768, 0, 'value_proj')
     bench(rows, 192, 768, 1, 'offsets+weights logits')
     bench(rows, 768, 768, 0, 'output_proj')

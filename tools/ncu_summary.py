@@ -41,24 +41,40 @@ def kernel(path):
 
 
 def launches(path):
+    """per kernel name: device time (share), and -- when the capture has them -- the time-weighted tensor-pipe
+    activity and the DRAM bytes per launch"""
     lines = [l for l in open(path) if not l.startswith('==')]
     tot, cnt = collections.defaultdict(float), collections.Counter()
-    n = 0
+    tens, dram = collections.defaultdict(float), collections.defaultdict(float)
+    per_id = collections.defaultdict(dict)
     for row in csv.DictReader(lines):
-        if row.get('Metric Name') != 'gpu__time_duration.sum':
-            continue
-        v = float(row['Metric Value'].replace(',', ''))
-        v = {'ns': v / 1e3, 'us': v, 'ms': v * 1e3, 's': v * 1e6}[row['Metric Unit']]
         k = re.sub(r'\(anonymous namespace\)::|<unnamed>::', '', row['Kernel Name'])
         k = re.sub(r'^void ', '', k)
         k = re.sub(r'\(.*', '', k)[:100]
-        tot[k] += v
+        v = float(row['Metric Value'].replace(',', ''))
+        per_id[(row['ID'], k)][row['Metric Name']] = (v, row['Metric Unit'])
+    n = 0
+    for (_, k), m in per_id.items():
+        if 'gpu__time_duration.sum' not in m:
+            continue
+        v, unit = m['gpu__time_duration.sum']
+        us = {'ns': v / 1e3, 'us': v, 'ms': v * 1e3, 's': v * 1e6}[unit]
+        tot[k] += us
         cnt[k] += 1
         n += 1
+        t = m.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')
+        if t:
+            tens[k] += t[0] * us
+        for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            if name in m:
+                b, bu = m[name]
+                dram[k] += b * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[bu]
     T = sum(tot.values())
     print(f'{n} launches, {T / 1e3:.2f} ms total device time (ncu: serialised, cold cache -- compare SHARES)')
-    for k, v in sorted(tot.items(), key=lambda x: -x[1])[:40]:
-        print(f'{v / 1e3:10.3f} ms {100 * v / T:6.2f}%  x{cnt[k]:5d}  avg {v / cnt[k]:10.1f} us  {k}')
+    print('   time      share   launches   avg us   tensor-pipe %   DRAM MB/launch   kernel')
+    for k, v in sorted(tot.items(), key=lambda x: -x[1])[:45]:
+        print(f'{v / 1e3:8.3f} ms {100 * v / T:6.2f}%  x{cnt[k]:4d} {v / cnt[k]:9.1f} {tens[k] / v if v else 0:10.1f} '
+              f'{dram[k] / cnt[k] / 1e6:14.1f}     {k}')
 
 
 if __name__ == '__main__':

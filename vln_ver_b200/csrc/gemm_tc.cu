@@ -240,6 +240,212 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ================================================================================================================
+// Two-CTA form (tcgen05 cta_group::2): a cluster of two CTAs owns a 256 x 256 output tile.  CTA r holds rows
+// [128 r, 128 r + 128) of the A tile and rows [128 r, 128 r + 128) of the W tile (half of the N = 256 columns), the
+// leader CTA issues ONE tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16) for the pair, and each CTA's tensor
+// memory receives its 128 accumulator rows.  Per SM and k-block that is 32 KB of operands written and read instead
+// of 48 KB: the single-CTA kernel above is shared-memory-bandwidth bound at ~70 % of the tensor peak
+// (profiles/r02f_gemm_check.txt), this form is what lifts that bound.
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (shared::cluster address with the CTA-rank bit
+//     cleared), which expects the bytes of both;
+//   * tcgen05.commit ... multicast::cluster arrives on the empty / accumulator-full barriers of BOTH CTAs;
+//   * the epilogue warps of both CTAs arrive on the LEADER's accumulator-empty barrier (remote mbarrier.arrive).
+constexpr int kG2Stages = 4, kG2N = 256;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address (rank 0 = leader)
+
+struct Gemm2Smem {
+    static constexpr int a_bytes = kGM * kGK * 2, b_bytes = (kG2N / 2) * kGK * 2, stage_bytes = a_bytes + b_bytes;
+    static constexpr int c_pitch = kG2N * 2 + 16, c_bytes = kGM * c_pitch;
+    static constexpr int off_c = kG2Stages * stage_bytes, off_bias = off_c + c_bytes;
+    static constexpr int total = off_bias + kG2N * 4 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db),
+        "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGThreads, 1)
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const float* __restrict__ bias, void* __restrict__ out, int M, int N, int K, int ldo, float p_drop,
+                uint64_t seed, const unsigned long long* __restrict__ seed_epoch) {
+    static_assert(EPI != kEpiBiasF32, "the two-CTA kernel writes fp16");
+    using S = Gemm2Smem;
+    constexpr int BN = kG2N;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[kG2Stages], bar_empty[kG2Stages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    if (tid == 0) {
+        for (int i = 0; i < kG2Stages; ++i) {
+            mbar_init(&bar_full[i], 1);                     // leader's: one arrive.expect_tx (+ the bytes of both CTAs)
+            mbar_init(&bar_empty[i], 1);                    // multicast commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_tfull[i], 1);                    // multicast commit
+            mbar_init(&bar_tempty[i], 2 * kGEpiWarps);      // leader's: the epilogue warps of both CTAs
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                     // the peer's barriers are initialised too
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const int n_blocks = N / BN, m_blocks = (M + 2 * kGM - 1) / (2 * kGM), tiles = n_blocks * m_blocks, kblocks = K / kGK;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer (both CTAs)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = cluster_id; t < tiles; t += n_clusters) {
+                const int mb = t / n_blocks, nb = t % n_blocks;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t st = it % kG2Stages, use = it / kG2Stages;
+                    if (use) gemm_wait(&bar_empty[st], (use - 1) & 1);
+                    unsigned char* sa = smem + st * S::stage_bytes;
+                    if (rank == 0) mbar_expect_tx(&bar_full[st], 2 * S::stage_bytes);
+                    tma_load_2d_2sm(sa, &map_a, kb * kGK, mb * 2 * kGM + (int)rank * kGM, &bar_full[st]);
+                    tma_load_2d_2sm(sa + S::a_bytes, &map_b, kb * kGK, nb * BN + (int)rank * (BN / 2), &bar_full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer (leader CTA, one lane)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc(2 * kGM, BN, 0, 0);
+            uint32_t it = 0, tile_i = 0;
+            for (int t = cluster_id; t < tiles; t += n_clusters, ++tile_i) {
+                const uint32_t as = tile_i & 1, ause = tile_i >> 1;
+                if (ause) gemm_wait(&bar_tempty[as], (ause - 1) & 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem + as * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t st = it % kG2Stages, use = it / kG2Stages;
+                    gemm_wait(&bar_full[st], use & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + st * S::stage_bytes);
+                    const uint64_t da = gemm_desc_sw128(sa), db = gemm_desc_sw128(sa + S::a_bytes);
+#pragma unroll
+                    for (int k = 0; k < kGK / 16; ++k)
+                        umma_f16_2sm(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_2sm(&bar_empty[st]);
+                }
+                umma_commit_2sm(&bar_tfull[as]);
+            }
+        }
+    } else {
+        // ================================================================ epilogue (both CTAs, own 128 rows)
+        const int q = warp & 3, row_in_tile = q * 32 + lane, ew = warp - 2;
+        constexpr int kColsPerWarp = BN / (kGEpiWarps / 4);
+        const int col_lo = (ew >> 2) * kColsPerWarp;
+        const uint32_t thr16 = (uint32_t)(p_drop * 65536.f);
+        const float scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+        if (EPI == kEpiBiasReluDropoutF16 && seed_epoch) seed += *seed_epoch;
+        float* s_bias = reinterpret_cast<float*>(smem + S::off_bias);
+        unsigned char* s_c = smem + S::off_c;
+        uint32_t tile_i = 0;
+        for (int t = cluster_id; t < tiles; t += n_clusters, ++tile_i) {
+            const int mb = t / n_blocks, nb = t % n_blocks;
+            const uint32_t as = tile_i & 1, ause = tile_i >> 1;
+            for (int i = tid - 64; i < BN; i += 32 * kGEpiWarps) s_bias[i] = bias ? __ldg(bias + nb * BN + i) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
+            gemm_wait(&bar_tfull[as], ause & 1);
+            tc_fence_after();
+            const int row0 = mb * 2 * kGM + (int)rank * kGM, row = row0 + row_in_tile;
+            const uint32_t taddr = tmem + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = col_lo; c0 < col_lo + kColsPerWarp; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                if (c0 + 32 >= col_lo + kColsPerWarp) {       // my last read of this accumulator stage
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
+                }
+                const int col = nb * BN + c0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += s_bias[c0 + i];
+                if (EPI == kEpiBiasReluDropoutF16) {
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const uint32_t m = p_drop > 0.f ? keep8((uint64_t)row * N + col + g8 * 8, seed, thr16) : 0xffu;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float x = v[g8 * 8 + e];
+                            v[g8 * 8 + e] = (((m >> e) & 1u) && x > 0.f) ? x * scale : 0.f;
+                        }
+                    }
+                }
+                unsigned char* dst = s_c + row_in_tile * S::c_pitch + c0 * 2;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 u;
+                    __half2 h;
+                    h = __floats2half2_rn(v[8 * i], v[8 * i + 1]);
+                    u.x = *reinterpret_cast<const uint32_t*>(&h);
+                    h = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+                    u.y = *reinterpret_cast<const uint32_t*>(&h);
+                    h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
+                    u.z = *reinterpret_cast<const uint32_t*>(&h);
+                    h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+                    u.w = *reinterpret_cast<const uint32_t*>(&h);
+                    reinterpret_cast<uint4*>(dst)[i] = u;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
+            unsigned char* out_b = reinterpret_cast<unsigned char*>(out);
+            for (int r = ew; r < kGM; r += kGEpiWarps) {
+                const int grow = row0 + r;
+                if (grow >= M) break;
+                unsigned char* gdst = out_b + ((size_t)grow * ldo + (size_t)nb * BN) * 2;
+                const unsigned char* src = s_c + r * S::c_pitch;
+                *reinterpret_cast<uint4*>(gdst + lane * 16) = *reinterpret_cast<const uint4*>(src + lane * 16);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                     // nobody leaves while the peer may still signal its barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 // ---------------------------------------------------------------- host: tensor maps through the driver entry point
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -298,7 +504,35 @@ int launch_gemm(const void* a, int lda, const void* w, int ldw, const float* bia
     return VER_OK;
 }
 
+template <int EPI>
+int launch_gemm2(const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldo, int M, int N,
+                 int K, float p_drop, uint64_t seed, const uint64_t* seed_epoch, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, a, M, K, lda, kGM);
+    if (rc) return rc;
+    rc = make_map(&mb, w, N, K, ldw, kG2N / 2);
+    if (rc) return rc;
+    auto kern = gemm2_tn_kernel<EPI>;
+    VER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem::total));
+    const int tiles = (N / kG2N) * ((M + 2 * kGM - 1) / (2 * kGM));
+    int ctas = ver_device_sm_count() & ~1;
+    if (2 * tiles < ctas) ctas = 2 * tiles;
+    kern<<<ctas, kGThreads, Gemm2Smem::total, st>>>(ma, mb, bias, out, M, N, K, ldo, p_drop, seed,
+                                                   (const unsigned long long*)seed_epoch);
+    VER_CHECK_LAUNCH();
+    g_ver_launches += 1;
+    return VER_OK;
+}
+
+// 0 = choose (two-CTA kernel where it applies), 1 = single-CTA kernel, 2 = two-CTA kernel (tests / tools A-B)
+int g_gemm_variant = 0;
+
 }  // namespace
+
+extern "C" int ver_debug_gemm_variant(int v) {
+    g_gemm_variant = v;
+    return VER_OK;
+}
 
 extern "C" int ver_linear_supported(int M, int N, int K) {
     return M > 0 && K > 0 && K % kGK == 0 && N > 0 && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0);
@@ -322,6 +556,11 @@ extern "C" int ver_linear_f16(int epilogue, const void* a, int lda, const void* 
      : epilogue == 1 ? launch_gemm<BN, kEpiBiasF32>(a, lda, w, ldw, bias, out, ldo, M, N, K, 0.f, 0, nullptr, st)         \
                      : launch_gemm<BN, kEpiBiasReluDropoutF16>(a, lda, w, ldw, bias, out, ldo, M, N, K, p_drop, seed,     \
                                                                seed_epoch, st))
+    if (N % 256 == 0 && epilogue != 1 && g_gemm_variant != 1) {       // two CTAs per 256 x 256 tile
+        if (epilogue == 0)
+            return launch_gemm2<kEpiBiasF16>(a, lda, w, ldw, bias, out, ldo, M, N, K, 0.f, 0, nullptr, st);
+        return launch_gemm2<kEpiBiasReluDropoutF16>(a, lda, w, ldw, bias, out, ldo, M, N, K, p_drop, seed, seed_epoch, st);
+    }
     // (the fp32 staging tile of a 256-column block does not fit next to the operand ring)
     if (N % 256 == 0 && epilogue != 1) return GEMM_BN(256);
     if (N % 192 == 0) return GEMM_BN(192);

@@ -305,6 +305,22 @@ class VoxelFormerOccupancyHead(PrecisionMixin, BaseModule):
         loss = torch.stack(losses).mean()
         return {'loss_occupancy': loss, 'loss_flow': torch.zeros_like(loss)}
 
+    def loss(self, gt_bboxes_list, gt_labels_list, point_coords, occ_gts, flow_gts, preds_dicts,
+             gt_bboxes_ignore=None, img_metas=None):
+        """Default-branch loss (only_occ=False, HEAD:1284-1385) restricted to the hot path's share of it: the
+        occupancy term the reference computes in the LAST decoder layer's loss_single (dense target filled with
+        class `occupancy_classes`, sparse GT scattered in, avg_factor = number of occupied voxels, sigmoid focal loss,
+        nan_to_num -- HEAD:1324-1332 and :977-986; the same arithmetic as loss_only_occupancy, :1386-1444) and the
+        zero flow term (`loss_flow = zeros_like`, :982).  Keys follow the reference's loss dict (:1355-1357: the last
+        decoder layer's entries are un-prefixed).  The detection terms (loss_cls / loss_bbox per decoder layer:
+        Hungarian assignment, L1 / GIoU) are outside the lift+encode path and are not computed:
+        asking for them raises."""
+        if preds_dicts.get('occupancy_preds') is None:
+            raise NotImplementedError('only the occupancy / flow terms of the default-branch loss are on the hot path; '
+                                      'the detection losses (HEAD:1336-1353) are out of scope')
+        return self.loss_only_occupancy(gt_bboxes_list, gt_labels_list, point_coords, occ_gts, flow_gts, preds_dicts,
+                                        gt_bboxes_ignore=gt_bboxes_ignore, img_metas=img_metas)
+
     # ------------------------------------------------------------------ A12
     def get_occupancy_prediction(self, occ_results, occ_threshold=0.25):
         if self.occ_loss_type != 'focal_loss':
