@@ -251,6 +251,18 @@ int ver_linear_supported(int M, int N, int K);
 int ver_linear_f16(int epilogue, const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldo,
                    int M, int N, int K, float p_drop, uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream);
 
+/* Backward of the FFN's second Linear fused with the backward of Dropout and ReLU and with the bias gradient of the
+ * first Linear (mmcv FFN, M/custom_base_transformer_layer.py:157-158; autograd of Linear -> ReLU -> Dropout -> Linear):
+ *     da[M, N] = (dy[M, K] @ w[N, K]^T) * [h > 0] / (1 - p_drop)          (two-CTA tcgen05 GEMM, csrc/gemm_tc.cu)
+ *     colsum_part[r, :] = column sums of da over the 128 rows of row block r   (fold with ver_colsum_fold -> bias gradient)
+ *   dy      fp16 gradient of the second Linear's output;   w = W2^T as [N = hidden, K = embed] fp16 row-major
+ *   h       fp16 saved output of the Dropout (> 0 exactly where the unit was positive and kept), leading dimension ld
+ *   da      fp16, leading dimension ld;   colsum_part fp32 [ver_linear_bwd_colsum_rows(M), N]
+ *   requires K % 64 == 0, N % 256 == 0. */
+int ver_linear_bwd_colsum_rows(int M);
+int ver_linear_relu_dropout_bwd_f16(const void* dy, int lddy, const void* w, int ldw, const void* h, void* da, int ld,
+                                    float* colsum_part, int M, int N, int K, float p_drop, ver_stream_t stream);
+
 /* FFN inner activation (mmcv FFN: Linear -> ReLU -> Dropout): h = dropout(relu(a)), in place allowed;
  * backward da = dh * [h > 0] / (1 - p).  n % 8 == 0.
  * Column sums (bias gradients) come as partial sums: colsum_part is [ver_colsum_partial_rows(), 8] fp32 and row t

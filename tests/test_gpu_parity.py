@@ -940,3 +940,29 @@ def test_linear_tc_vs_fp32_reference(M, N, K, epi, p):
     assert rel_err(out, ref) < (1e-5 if epi == ops.LINEAR_BIAS_F32 else 1e-3)
     with pytest.raises(ops.VerError):
         ops.linear_tc(x[:, :K - 8].contiguous(), w[:, :K - 8].contiguous(), b)      # K % 64 != 0
+
+
+@pytest.mark.parametrize('M,N,K,p', [(300, 256, 64, 0.0), (5000, 512, 256, 0.1), (2600, 1536, 768, 0.1)])
+def test_linear_relu_dropout_backward_fused_gemm(M, N, K, p):
+    """ver_linear_relu_dropout_bwd_f16: dX of the FFN's second Linear fused with the Dropout / ReLU backward and the
+    column sums that are the first Linear's bias gradient (autograd of mmcv's FFN,
+    M/custom_base_transformer_layer.py:157-158), against torch autograd in fp32 on the same fp16 operands."""
+    from vln_ver_b200 import fused_layer as FL
+    g = torch.Generator(device=DEV).manual_seed(N + K)
+    dy = (torch.randn(M, K, device=DEV, generator=g) * 0.1).half()          # gradient of the second Linear's output
+    w2 = (torch.randn(K, N, device=DEV, generator=g) * 0.05).half()         # second Linear's weight [out = K, in = N]
+    a = torch.randn(M, N, device=DEV, generator=g)
+    keep = (torch.rand(M, N, device=DEV, generator=g) >= p)
+    h = (torch.relu(a) * keep / (1 - p)).half()                             # saved Dropout output
+    da, part = ops.linear_relu_dropout_bwd(dy, w2.t().contiguous(), h, p)
+    ref = (dy.float() @ w2.float()) * (h > 0) / (1 - p)
+    assert rel_err(da, ref) < 1e-3
+    assert part.shape == (_lib_rows(M), N)
+    cs = FL._fold_rows(part)
+    assert rel_err(cs, da.float().sum(0)) < 1e-5                             # sums of what the kernel stored
+    assert rel_err(cs, ref.sum(0)) < 2e-3
+
+
+def _lib_rows(M):
+    from vln_ver_b200._lib import lib as _l
+    return _l.ver_linear_bwd_colsum_rows(M)

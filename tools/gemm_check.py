@@ -79,6 +79,44 @@ def bench(M, N, K, epi, name):
           flush=True)
 
 
+def bench_bwd(M, N, K, p=0.1):
+    """dX of FFN2 + ReLU / dropout backward + column sums: fused two-CTA GEMM against library GEMM + ver_relu_dropout_bwd"""
+    from vln_ver_b200 import fused_layer as FL
+    g = torch.Generator(device='cuda').manual_seed(2)
+    dy = (torch.randn(M, K, device='cuda', generator=g) * 0.1).half()
+    w2 = (torch.randn(K, N, device='cuda', generator=g) * 0.05).half()
+    h = (torch.relu(torch.randn(M, N, device='cuda', generator=g)) * (torch.rand(M, N, device='cuda', generator=g) >= p) / (1 - p)).half()
+    w2t = w2.t().contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+    def t(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(10):
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def own():
+        da, part = ops.linear_relu_dropout_bwd(dy, w2t, h, p)
+        return FL._fold_rows(part)
+
+    def lib_fn():
+        dh = torch.mm(dy, w2)
+        return FL._relu_dropout_bwd_(dh, h, p)
+    t_own, t_lib = t(own), t(lib_fn)
+    fl = 2.0 * M * N * K
+    print(f'FFN2 dX + ReLU/dropout bwd + colsum M={M:6d} N={N:4d} K={K:4d}: tcgen05 fused {t_own * 1e3:7.1f} us '
+          f'({fl / t_own / 1e9:6.0f} TFLOP/s)   library GEMM + relu_dropout_bwd pass {t_lib * 1e3:7.1f} us', flush=True)
+
+
 def main():
     _lib.lib.ver_debug_gemm_variant.argtypes = [__import__('ctypes').c_int]
     ok = True
@@ -111,6 +149,7 @@ def main():
         bench(rows, 768, 1536, 0, 'FFN2')
     _lib.lib.ver_debug_gemm_variant(0)
     bench(rows, 192, 768, 1, 'offsets+weights logits')
+    bench_bwd(rows, 1536, 768)
     return
     bench(8 * 18 * 196, 768, 768, 0, 'value_proj')
     bench(rows, 192, 768, 1, 'offsets+weights logits')

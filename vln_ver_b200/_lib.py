@@ -65,6 +65,8 @@ def _load():
         'ver_linear_supported': (c_int, [c_int, c_int, c_int]),
         'ver_linear_f16': (c_int, [c_int, P, c_int, P, c_int, P, P, c_int, c_int, c_int, c_int, c_float,
                                    ctypes.c_uint64, P, P]),
+        'ver_linear_bwd_colsum_rows': (c_int, [c_int]),
+        'ver_linear_relu_dropout_bwd_f16': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_float, P]),
         'ver_colsum_partial_rows': (c_int, []),
         'ver_relu_dropout_bwd': (c_int, [c_int, P, P, P, c_int64, c_float, c_int, P, P]),
         'ver_cast_colsum': (c_int, [c_int, P, P, c_int64, c_int, P, P]),

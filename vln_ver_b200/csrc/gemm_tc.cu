@@ -33,7 +33,7 @@ constexpr int kGM = 128, kGK = 64, kGStages = 3;
 constexpr int kGEpiWarps = 8;                    // two per TMEM lane quarter: each takes half of the tile's columns
 constexpr int kGThreads = 64 + 32 * kGEpiWarps;
 
-enum GemmEpilogue { kEpiBiasF16 = 0, kEpiBiasF32 = 1, kEpiBiasReluDropoutF16 = 2 };
+enum GemmEpilogue { kEpiBiasF16 = 0, kEpiBiasF32 = 1, kEpiBiasReluDropoutF16 = 2, kEpiMaskColsumF16 = 3 };
 
 template <int BN, int ESIZE>
 struct GemmSmem {
@@ -256,9 +256,11 @@ constexpr uint32_t kPeerMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of
 
 struct Gemm2Smem {
     static constexpr int a_bytes = kGM * kGK * 2, b_bytes = (kG2N / 2) * kGK * 2, stage_bytes = a_bytes + b_bytes;
-    static constexpr int c_pitch = kG2N * 2 + 16, c_bytes = kGM * c_pitch;
+    // output staging: two buffers of one column half (128 rows x 128 columns fp16 = two 128-byte-swizzled TMA boxes)
+    static constexpr int half_bytes = 2 * kGM * 128, c_bytes = 2 * half_bytes;
     static constexpr int off_c = kG2Stages * stage_bytes, off_bias = off_c + c_bytes;
-    static constexpr int total = off_bias + kG2N * 4 + 1024;
+    static constexpr int off_cs = off_bias + kG2N * 4;                       // [2][4 row groups][128] fp32 column sums
+    static constexpr int total = off_cs + 2 * 4 * 128 * 4 + 1024;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -295,14 +297,16 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGThreads, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const float* __restrict__ bias, void* __restrict__ out, int M, int N, int K, int ldo, float p_drop,
-                uint64_t seed, const unsigned long long* __restrict__ seed_epoch) {
+                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_h,
+                const float* __restrict__ bias, int M, int N, int K, int ldo, float p_drop,
+                uint64_t seed, const unsigned long long* __restrict__ seed_epoch, const __half* __restrict__ aux,
+                float* __restrict__ colsum_part) {
     static_assert(EPI != kEpiBiasF32, "the two-CTA kernel writes fp16");
     using S = Gemm2Smem;
     constexpr int BN = kG2N;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bar_full[kG2Stages], bar_empty[kG2Stages], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[kG2Stages], bar_empty[kG2Stages], bar_tfull[2], bar_tempty[2], bar_h[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
@@ -314,6 +318,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_tfull[i], 1);                    // multicast commit
             mbar_init(&bar_tempty[i], 2 * kGEpiWarps);      // leader's: the epilogue warps of both CTAs
+            mbar_init(&bar_h[i], 1);                        // mask operand of a half landed in staging buffer i
         }
         mbar_fence_init();
     }
@@ -371,74 +376,164 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else {
         // ================================================================ epilogue (both CTAs, own 128 rows)
-        const int q = warp & 3, row_in_tile = q * 32 + lane, ew = warp - 2;
-        constexpr int kColsPerWarp = BN / (kGEpiWarps / 4);
-        const int col_lo = (ew >> 2) * kColsPerWarp;
+        // The tile leaves in two column halves of 128: a half is staged in shared memory as two TMA boxes
+        // (128 rows x 64 columns, 128-byte swizzle: a thread writing its row's 16-byte pieces is conflict free) and
+        // stored by ONE asynchronous TMA store per box; two staging buffers, so the store of a half runs under the
+        // epilogue math of the next one (the first version copied rows out with the epilogue warps themselves and was
+        // epilogue bound: profiles/r02h_gemm_check.txt).  Warp (quarter q, box x): rows 32 q .., box x of the half.
+        const int q = warp & 3, row_in_tile = q * 32 + lane, ew = warp - 2, box = ew >> 2;
         const uint32_t thr16 = (uint32_t)(p_drop * 65536.f);
         const float scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
         if (EPI == kEpiBiasReluDropoutF16 && seed_epoch) seed += *seed_epoch;
         float* s_bias = reinterpret_cast<float*>(smem + S::off_bias);
-        unsigned char* s_c = smem + S::off_c;
-        uint32_t tile_i = 0;
+        float* s_cs = reinterpret_cast<float*>(smem + S::off_cs);              // [2 (half parity)][4 row groups][128]
+        const bool issuer = tid == 64;
+        // (mask epilogue) the saved activation's half tile is TMA-loaded into the staging buffer the half will be
+        // written to, one half ahead: coalesced, asynchronous, and read back at the same swizzled positions
+        auto load_h = [&](int tt, int half, uint32_t buf) {
+            const int mb2 = tt / n_blocks, nb2 = tt % n_blocks;
+            unsigned char* dstb = smem + S::off_c + buf * S::half_bytes;
+            mbar_expect_tx(&bar_h[buf], S::half_bytes);
+#pragma unroll
+            for (int x = 0; x < 2; ++x)
+                tma_load_2d(dstb + x * (kGM * 128), &map_h, nb2 * BN + half * 128 + x * 64, mb2 * 2 * kGM + (int)rank * kGM,
+                            &bar_h[buf]);
+        };
+        if (EPI == kEpiMaskColsumF16 && issuer && cluster_id < tiles) load_h(cluster_id, 0, 0);
+        uint32_t tile_i = 0, half_i = 0;
         for (int t = cluster_id; t < tiles; t += n_clusters, ++tile_i) {
             const int mb = t / n_blocks, nb = t % n_blocks;
             const uint32_t as = tile_i & 1, ause = tile_i >> 1;
-            for (int i = tid - 64; i < BN; i += 32 * kGEpiWarps) s_bias[i] = bias ? __ldg(bias + nb * BN + i) : 0.f;
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
-            gemm_wait(&bar_tfull[as], ause & 1);
-            tc_fence_after();
             const int row0 = mb * 2 * kGM + (int)rank * kGM, row = row0 + row_in_tile;
             const uint32_t taddr = tmem + as * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = col_lo; c0 < col_lo + kColsPerWarp; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
-                if (c0 + 32 >= col_lo + kColsPerWarp) {       // my last read of this accumulator stage
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
+            for (int half = 0; half < 2; ++half, ++half_i) {
+                unsigned char* s_h = smem + S::off_c + (half_i & 1) * S::half_bytes;          // staging buffer of this half
+                // buffer (half_i & 1) was last stored two halves ago: its TMA store must have finished READING it
+                // (mask epilogue: already waited for when the mask operand was loaded into it)
+                if (EPI != kEpiMaskColsumF16 && issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (half == 0)
+                    for (int i = tid - 64; i < BN; i += 32 * kGEpiWarps) s_bias[i] = bias ? __ldg(bias + nb * BN + i) : 0.f;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
+                if (half == 0) {
+                    gemm_wait(&bar_tfull[as], ause & 1);
+                    tc_fence_after();
                 }
-                const int col = nb * BN + c0;
+                unsigned char* s_box = s_h + box * (kGM * 128) + row_in_tile * 128;
+#pragma unroll 1
+                for (int cc = 0; cc < 64; cc += 32) {
+                    const int c0 = half * 128 + box * 64 + cc;                 // column inside the tile
+                    float v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (half == 1 && cc == 32) {                               // my last read of this accumulator stage
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&bar_tempty[as]);
+                    }
+                    const int col = nb * BN + c0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += s_bias[c0 + i];
-                if (EPI == kEpiBiasReluDropoutF16) {
+                    for (int i = 0; i < 32; ++i) v[i] += s_bias[c0 + i];
+                    if (EPI == kEpiBiasReluDropoutF16) {
 #pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        const uint32_t m = p_drop > 0.f ? keep8((uint64_t)row * N + col + g8 * 8, seed, thr16) : 0xffu;
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const uint32_t m = p_drop > 0.f ? keep8((uint64_t)row * N + col + g8 * 8, seed, thr16) : 0xffu;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float x = v[g8 * 8 + e];
-                            v[g8 * 8 + e] = (((m >> e) & 1u) && x > 0.f) ? x * scale : 0.f;
+                            for (int e = 0; e < 8; ++e) {
+                                const float x = v[g8 * 8 + e];
+                                v[g8 * 8 + e] = (((m >> e) & 1u) && x > 0.f) ? x * scale : 0.f;
+                            }
+                        }
+                    }
+                    if (EPI == kEpiMaskColsumF16) {
+                        // ReLU / dropout backward: the saved activation is > 0 exactly where the unit was kept and
+                        // positive; its tile sits in this staging buffer (rows past M: zero filled by TMA)
+                        if (cc == 0) gemm_wait(&bar_h[half_i & 1], (half_i >> 1) & 1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int chunk = (cc >> 3) + i;
+                            const uint4 hv = *reinterpret_cast<const uint4*>(s_box + ((chunk ^ (row_in_tile & 7)) << 4));
+                            const __half2* hh = reinterpret_cast<const __half2*>(&hv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(hh[e]);
+                                v[8 * i + 2 * e] = f.x > 0.f ? v[8 * i + 2 * e] * scale : 0.f;
+                                v[8 * i + 2 * e + 1] = f.y > 0.f ? v[8 * i + 2 * e + 1] * scale : 0.f;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 u;
+                        __half2 h;
+                        h = __floats2half2_rn(v[8 * i], v[8 * i + 1]);
+                        u.x = *reinterpret_cast<const uint32_t*>(&h);
+                        h = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+                        u.y = *reinterpret_cast<const uint32_t*>(&h);
+                        h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
+                        u.z = *reinterpret_cast<const uint32_t*>(&h);
+                        h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+                        u.w = *reinterpret_cast<const uint32_t*>(&h);
+                        const int chunk = (cc >> 3) + i;                        // 16-byte piece 0..7 of my 128-byte row
+                        *reinterpret_cast<uint4*>(s_box + ((chunk ^ (row_in_tile & 7)) << 4)) = u;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // staged bytes -> visible to the TMA engine
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
+                if (issuer) {
+                    const int gc = nb * BN + half * 128;
+#pragma unroll
+                    for (int x = 0; x < 2; ++x)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
+                                     "r"(smem_u32(s_h + x * (kGM * 128))), "r"(gc + x * 64), "r"(row0)
+                                     : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (EPI == kEpiMaskColsumF16) {
+                        // next half's mask operand -> the other buffer, once the store that last used it was read out
+                        const int nt = half == 0 ? t : t + n_clusters, nh = half ^ 1;
+                        if (nt < tiles) {
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            load_h(nt, nh, (half_i + 1) & 1);
                         }
                     }
                 }
-                unsigned char* dst = s_c + row_in_tile * S::c_pitch + c0 * 2;
+                if (EPI == kEpiMaskColsumF16) {
+                    // column sums of the staged half (rows past M hold zeros): warp = (box ew & 1, row group ew >> 1);
+                    // a lane keeps one 16-byte piece (8 columns) and walks 4 rows per step -- conflict free
+                    const int cbox = ew & 1, rg = ew >> 1, piece = lane & 7;
+                    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 u;
-                    __half2 h;
-                    h = __floats2half2_rn(v[8 * i], v[8 * i + 1]);
-                    u.x = *reinterpret_cast<const uint32_t*>(&h);
-                    h = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-                    u.y = *reinterpret_cast<const uint32_t*>(&h);
-                    h = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-                    u.z = *reinterpret_cast<const uint32_t*>(&h);
-                    h = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
-                    u.w = *reinterpret_cast<const uint32_t*>(&h);
-                    reinterpret_cast<uint4*>(dst)[i] = u;
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = rg * 32 + k * 4 + (lane >> 3);
+                        const uint4 u = *reinterpret_cast<const uint4*>(s_h + cbox * (kGM * 128) + r * 128 + ((piece ^ (r & 7)) << 4));
+                        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(hh[e]);
+                            cs[2 * e] += f.x;
+                            cs[2 * e + 1] += f.y;
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        cs[e] += __shfl_xor_sync(VER_FULL_MASK, cs[e], 8);
+                        cs[e] += __shfl_xor_sync(VER_FULL_MASK, cs[e], 16);
+                    }
+                    float* dst = s_cs + ((half_i & 1) * 4 + rg) * 128 + cbox * 64 + piece * 8;
+                    if (lane < 8) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) dst[e] = cs[e];
+                    }
+                    asm volatile("bar.sync 2, %0;" ::"n"(32 * kGEpiWarps) : "memory");
+                    if (tid - 64 < 128) {
+                        const int c = tid - 64;
+                        const float* src = s_cs + (half_i & 1) * 4 * 128 + c;
+                        colsum_part[(size_t)(mb * 2 + (int)rank) * N + nb * BN + half * 128 + c] =
+                            src[0] + src[128] + src[256] + src[384];
+                    }
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
-            unsigned char* out_b = reinterpret_cast<unsigned char*>(out);
-            for (int r = ew; r < kGM; r += kGEpiWarps) {
-                const int grow = row0 + r;
-                if (grow >= M) break;
-                unsigned char* gdst = out_b + ((size_t)grow * ldo + (size_t)nb * BN) * 2;
-                const unsigned char* src = s_c + r * S::c_pitch;
-                *reinterpret_cast<uint4*>(gdst + lane * 16) = *reinterpret_cast<const uint4*>(src + lane * 16);
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kGEpiWarps) : "memory");
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every store landed before the CTA leaves
     }
     tc_fence_before();
     __syncthreads();
@@ -506,19 +601,28 @@ int launch_gemm(const void* a, int lda, const void* w, int ldw, const float* bia
 
 template <int EPI>
 int launch_gemm2(const void* a, int lda, const void* w, int ldw, const float* bias, void* out, int ldo, int M, int N,
-                 int K, float p_drop, uint64_t seed, const uint64_t* seed_epoch, cudaStream_t st) {
+                 int K, float p_drop, uint64_t seed, const uint64_t* seed_epoch, cudaStream_t st,
+                 const void* aux = nullptr, float* colsum_part = nullptr) {
     CUtensorMap ma, mb;
     int rc = make_map(&ma, a, M, K, lda, kGM);
     if (rc) return rc;
     rc = make_map(&mb, w, N, K, ldw, kG2N / 2);
     if (rc) return rc;
+    CUtensorMap mc;                                     // output [M, N] fp16: 128 x 64 boxes, same swizzle as the staging
+    rc = make_map(&mc, out, M, N, ldo, kGM);
+    if (rc) return rc;
+    CUtensorMap mh = mc;                                // mask operand (same shape as the output) of the backward epilogue
+    if (aux) {
+        rc = make_map(&mh, aux, M, N, ldo, kGM);
+        if (rc) return rc;
+    }
     auto kern = gemm2_tn_kernel<EPI>;
     VER_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem::total));
     const int tiles = (N / kG2N) * ((M + 2 * kGM - 1) / (2 * kGM));
     int ctas = ver_device_sm_count() & ~1;
     if (2 * tiles < ctas) ctas = 2 * tiles;
-    kern<<<ctas, kGThreads, Gemm2Smem::total, st>>>(ma, mb, bias, out, M, N, K, ldo, p_drop, seed,
-                                                   (const unsigned long long*)seed_epoch);
+    kern<<<ctas, kGThreads, Gemm2Smem::total, st>>>(ma, mb, mc, mh, bias, M, N, K, ldo, p_drop, seed,
+                                                   (const unsigned long long*)seed_epoch, (const __half*)aux, colsum_part);
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;
@@ -533,6 +637,22 @@ extern "C" int ver_debug_gemm_variant(int v) {
     g_gemm_variant = v;
     return VER_OK;
 }
+
+/* da = (dy @ w^T) * [h > 0] / (1 - p_drop) and the column sums of da, see include/ver_b200.h */
+extern "C" int ver_linear_relu_dropout_bwd_f16(const void* dy, int lddy, const void* w, int ldw, const void* h, void* da,
+                                               int ld, float* colsum_part, int M, int N, int K, float p_drop,
+                                               ver_stream_t stream) {
+    VER_CHECK_ARG(dy && w && h && da && colsum_part, "null pointer");
+    VER_CHECK_ARG(M > 0 && K > 0 && K % kGK == 0 && N > 0 && N % kG2N == 0, "needs K %% 64 == 0 and N %% 256 == 0 (got N=%d K=%d)", N, K);
+    VER_CHECK_ARG(lddy >= K && ldw >= K && ld >= N && lddy % 8 == 0 && ldw % 8 == 0 && ld % 8 == 0, "leading dimensions");
+    VER_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)h & 15) == 0 && ((uintptr_t)da & 15) == 0,
+                  "operands must be 16-byte aligned");
+    VER_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "bad dropout probability");
+    return launch_gemm2<kEpiMaskColsumF16>(dy, lddy, w, ldw, nullptr, da, ld, M, N, K, p_drop, 0, nullptr,
+                                           (cudaStream_t)stream, h, colsum_part);
+}
+
+extern "C" int ver_linear_bwd_colsum_rows(int M) { return 2 * ((M + 2 * kGM - 1) / (2 * kGM)); }
 
 extern "C" int ver_linear_supported(int M, int N, int K) {
     return M > 0 && K > 0 && K % kGK == 0 && N > 0 && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0);

@@ -6,12 +6,14 @@
 
 namespace {
 
-// ---------------------------------------------------------------- Philox4x32-10
+// ---------------------------------------------------------------- Philox4x32-7
+// (7 rounds: the smallest round count of Philox4x32 that passes BigCrush (Salmon et al., SC'11); 10 is the library
+// default margin.  The masks only have to be unbiased and reproducible between forward and backward.)
 __device__ __forceinline__ uint4 philox4x32(uint64_t ctr, uint64_t seed) {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < 7; ++i) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;

@@ -37,7 +37,8 @@ _GENERATION = [0]
 # (N = 192, fp32 out) 95 us against 194 us, FFN1 with bias + ReLU + dropout fused 492 us against 644 us for library
 # GEMM + ver_relu_dropout_fwd; the three plain N = 768 projections are still 0.78-0.86x of the library (a single-CTA
 # 128 x 256 tile is shared-memory-bandwidth bound at ~70 % of the tensor peak), so they stay on the library.
-TC_GEMM = {'logits': True, 'ffn1': True, 'value_proj': False, 'output_proj': False, 'ffn2': False}
+TC_GEMM = {'logits': True, 'ffn1': True, 'value_proj': False, 'output_proj': False, 'ffn2': False,
+           'ffn2_bwd': True}      # backward of FFN2 fused with ReLU / dropout backward and the FFN1 bias gradient
 
 
 def invalidate_weight_cache():
@@ -75,6 +76,11 @@ def half_of(*params):
     """fp16 copy of a parameter (or the row-concatenation of several), refreshed when a parameter changes."""
     return _cached('f16', params, lambda: params[0].detach().to(torch.float16) if len(params) == 1 else
                    torch.cat([p.detach() for p in params], 0).to(torch.float16))
+
+
+def half_t_of(param):
+    """fp16 TRANSPOSED copy ([in, out] of an [out, in] Linear weight): the K-major W^T operand of a dX GEMM."""
+    return _cached('f16t', (param,), lambda: param.detach().to(torch.float16).t().contiguous())
 
 
 def f32_cat(*params):
@@ -292,6 +298,7 @@ class VoxelLayerFunction(Function):
             ctx.vis, ctx.dims = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP)
             ctx.drop = (p_attn, seed1, p_ffn, p_out, seed3)
             ctx.n_so = Wso.shape[0]
+            ctx.W2 = W2
             ctx.pdtypes = [t.dtype for t in (Wv, bv, Wso, bso, Waw, baw, Wo, bo, g1, be1, W1, b1, W2, b2, g2, be2)]
         return y2
 
@@ -311,9 +318,14 @@ class VoxelLayerFunction(Function):
         ops.nvtx_push('layer.bwd.ffn+norm')
         df, dy1, dg2, dbe2, db2 = _ln_bwd(dy2, z2, st2, g2f, p_out, seed3)
         dW2 = torch.mm(df.t(), h, out_dtype=f32)
-        dh = torch.mm(df, W216)
+        if (TC_GEMM['ffn2_bwd'] and ctx.W2 is not None and h.shape[1] % 256 == 0 and df.shape[1] % 64 == 0):
+            # dX of FFN2, ReLU / dropout backward and the column sums (= FFN1 bias gradient) in one tcgen05 GEMM
+            dh, part = ops.linear_relu_dropout_bwd(df, half_t_of(ctx.W2), h, p_ffn)
+            db1 = _fold_rows(part)
+        else:
+            dh = torch.mm(df, W216)
+            db1 = _relu_dropout_bwd_(dh, h, p_ffn)          # dh -> da in place
         del df
-        db1 = _relu_dropout_bwd_(dh, h, p_ffn)              # dh -> da in place
         dW1 = torch.mm(dh.t(), y1, out_dtype=f32)
         dy1.addmm_(dh, W116)                                # + residual branch, accumulated by the GEMM
         del dh

@@ -698,6 +698,21 @@ def linear_tc(x, weight, bias=None, epilogue=LINEAR_BIAS_F16, p=0.0, seed=0):
     return out
 
 
+def linear_relu_dropout_bwd(dy, w_t, h, p):
+    """da = (dy @ w_t^T) * [h > 0] / (1 - p) and its column sums as partial rows (fold -> bias gradient).
+    dy (M, K) fp16; w_t (N, K) fp16 = W2^T; h (M, N) fp16 -> da (M, N) fp16, part (row blocks, N) fp32."""
+    _need_cuda(dy, w_t, h)
+    dy, w_t, h = _c(dy), _c(w_t), _c(h)
+    M, K = dy.shape
+    N = w_t.shape[0]
+    assert w_t.shape[1] == K and h.shape == (M, N) and dy.dtype == w_t.dtype == h.dtype == torch.float16
+    da = torch.empty((M, N), dtype=torch.float16, device=dy.device)
+    part = torch.empty((lib.ver_linear_bwd_colsum_rows(M), N), dtype=torch.float32, device=dy.device)
+    check(lib.ver_linear_relu_dropout_bwd_f16(_ptr(dy), K, _ptr(w_t), K, _ptr(h), _ptr(da), N, _ptr(part), M, N, K,
+                                              float(p), _stream()))
+    return da, part
+
+
 # ------------------------------------------------------------------ A11, A12
 class _FocalFunction(Function):
     @staticmethod
