@@ -67,6 +67,8 @@ def main():
                 (4, 'sca_fwd_tc4_kernel', 'ver_debug_tc4_timing', names4)]
     if '--tc3' in sys.argv:
         variants.append((3, 'sca_fwd_tc3_kernel', 'ver_debug_tc3_timing', names3))
+    if '--bwd-only' in sys.argv:
+        variants = []
     for variant, kname, tname, names in variants:
         cur[0] = variant
         f3 = hook(tname)
@@ -103,8 +105,8 @@ def main():
     if '--fwd-only' in sys.argv:
         return
     # ---- backward: sca_bwd_tc2_kernel (two threads per hit, lane-interleaved Dots staging) vs sca_bwd_tc_kernel
-    names_b2 = {16: 'un-tap + hit ids', 18: "A' rows (+ G gather latency)", 17: 'G image stores',
-                19: 'fences, MMA issue, Dots MMAs', 20: 'Dots dump', 21: 'tap read-back, softmax bwd, atomics',
+    names_b2 = {16: 'un-tap + hit ids', 17: 'G image stores, Dots MMA issue', 18: "A' rows",
+                19: 'fences, dV^T MMA issue, wait Dots MMAs', 20: 'Dots dump', 21: 'tap read-back, softmax bwd, atomics',
                 23: 'wait dV^T MMAs', 22: 'dV^T -> grad_value'}
     _lib.lib.ver_debug_bwd_variant.restype = ctypes.c_int
     _lib.lib.ver_debug_bwd_variant.argtypes = [ctypes.c_int]

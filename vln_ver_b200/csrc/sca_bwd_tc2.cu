@@ -33,7 +33,7 @@ struct B2Smem {
         off_g = off_a + a_bytes;
         off_d = off_g + g_bytes;
         off_n = off_d + d_bytes;
-        total = off_n + 2 * kB2Hits * 4;
+        total = off_n + 3 * kB2Hits * 4;
     }
 };
 
@@ -95,6 +95,14 @@ __device__ __forceinline__ uint32_t ldg_pin(const uint32_t* p) {
     return v;
 }
 
+// vector reductions into global memory (sm_90+): one L2 operation per 16 / 8 bytes instead of one per float
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 // tent weight of a cell at signed distance d, and its derivative with respect to the coordinate
 __device__ __forceinline__ float tent(float d) { return fmaxf(1.f - fabsf(d), 0.f); }
 // (cell to the left of / at the coordinate: -1 on [0, 1); cell to the right: +1 on [-1, 0) -- the reference's
@@ -117,8 +125,8 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
     const B2Smem L(DH, SP);
     __half* Gimg = reinterpret_cast<__half*>(smem + L.off_g);
     float* dstage = reinterpret_cast<float*>(smem + L.off_d);
-    int* s_n = reinterpret_cast<int*>(smem + L.off_n);       // [2][128] hit -> voxel ids, double buffered
-    __shared__ __align__(8) uint64_t bar_v, bar_dots, bar_dv;
+    int* s_n = reinterpret_cast<int*>(smem + L.off_n);       // [3][128] hit -> voxel ids of chunks c, c + 1, c + 2 (c % 3)
+    __shared__ __align__(8) uint64_t bar_v, bar_dots, bar_dv, bar_g;
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,6 +157,7 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         mbar_init(&bar_v, 1);
         mbar_init(&bar_dots, 1);
         mbar_init(&bar_dv, 1);
+        mbar_init(&bar_g, kB2Threads);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(&s_tmem, 512);
@@ -180,6 +189,7 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
     const uint32_t myrow = smem_u32(smem + L.off_a) + (uint32_t)(r >> 3) * G * 128u + (uint32_t)(r & 7) * 16u;
     const float* my_dots = dstage + ((size_t)(r >> 5) * SP) * 32 + (r & 31);       // column c at + c * 32
     int tap_pix[PPT];
+    uint32_t tap_o01[PPT], tap_o23[PPT];          // byte offsets of the four cells of each tap, 16 bits each
     bool tapped = false;
 
     uint32_t phase = 0;
@@ -218,31 +228,37 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
     };
     int n_cur = r < nitems ? idx[r] : -1, n_nx = kB2Hits + r < nitems ? idx[kB2Hits + r] : -1;
     RowData d_cur, d_nx;
-    uint4 g_cur[kG], g_nx[kG];
-    if (tid < kB2Hits) s_n[tid] = tid < nitems ? idx[tid] : -1;
-    int sn_pref = (tid < kB2Hits && kB2Hits + tid < nitems) ? idx[kB2Hits + tid] : -1;     // row tid of chunk 1
+    uint4 g_cur[kG];
+    int sn_pref = -1;                                                                       // row tid of chunk c + 2
+    if (tid < kB2Hits) {
+        s_n[tid] = tid < nitems ? idx[tid] : -1;
+        s_n[kB2Hits + tid] = kB2Hits + tid < nitems ? idx[kB2Hits + tid] : -1;
+        sn_pref = 2 * kB2Hits + tid < nitems ? idx[2 * kB2Hits + tid] : -1;
+    }
     load_row(n_cur, d_cur);
     __syncthreads();
     load_g(s_n, g_cur);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int base = chunk * kB2Hits;
-        int* sn_next = s_n + ((chunk + 1) & 1) * kB2Hits;
         // ---- un-tap my points of the previous chunk (its MMAs retired); prefetches
         if (tapped) {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
-                const int k = tap_pix[p];
-                b2_sts16(myrow + koffb(k), 0);
-                b2_sts16(myrow + koffb(k + 1), 0);
-                b2_sts16(myrow + koffb(k + Sw), 0);
-                b2_sts16(myrow + koffb(k + Sw + 1), 0);
+                b2_sts16(myrow + (tap_o01[p] & 0xffffu), 0);
+                b2_sts16(myrow + (tap_o01[p] >> 16), 0);
+                b2_sts16(myrow + (tap_o23[p] & 0xffffu), 0);
+                b2_sts16(myrow + (tap_o23[p] >> 16), 0);
             }
             tapped = false;
         }
+        // ---- prefetches for the next chunk.  Measured placements (profiles/r02m): here, 877 us per launch; after the
+        // iteration's second proxy fence, 926 us; two chunks ahead in a second register set, 953 us -- the issue of
+        // these per-hit gathers (16 cache lines per warp instruction) costs the same ~2 300 cycles wherever it stands,
+        // and a proxy fence waits for the loads in flight
         if (tid < kB2Hits) {
-            sn_next[tid] = sn_pref;                  // loaded one chunk ago
-            sn_pref = base + 2 * kB2Hits + tid < nitems
-                          ? (int)ldg_pin(reinterpret_cast<const uint32_t*>(idx + base + 2 * kB2Hits + tid))
+            s_n[((chunk + 2) % 3) * kB2Hits + tid] = sn_pref;          // ids of chunk + 2, loaded one chunk ago
+            sn_pref = base + 3 * kB2Hits + tid < nitems
+                          ? (int)ldg_pin(reinterpret_cast<const uint32_t*>(idx + base + 3 * kB2Hits + tid))
                           : -1;
         }
         load_row(n_nx, d_nx);
@@ -250,6 +266,34 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                              ? (int)ldg_pin(reinterpret_cast<const uint32_t*>(idx + base + 2 * kB2Hits + r))
                              : -1;
         tb.lap(16);                                  // un-tap + prefetch issue
+        // ---- this chunk's grad_slots rows -> G image (its last readers, the previous chunk's dV^T MMAs, retired).
+        // Dots = G V^T does not depend on A': thread 0 issues those MMAs as soon as every thread stored its part,
+        // and they run while the A' rows are built
+#pragma unroll
+        for (int u = 0; u < kG; ++u) {
+            const int i = tid + u * kB2Threads;
+            if (i < kB2Hits * CG) {
+                const int rr = i / CG, cg = i % CG;
+                *reinterpret_cast<uint4*>(Gimg + ((rr >> 3) * CG + cg) * 64 + (rr & 7) * 8) = g_cur[u];
+            }
+        }
+        // the next chunk's grad_slots rows (ids published one chunk ago): in flight for a whole chunk
+        load_g(s_n + ((chunk + 1) % 3) * kB2Hits, g_cur);
+        proxy_fence();
+        tc_fence_before();
+        mbar_arrive(&bar_g);
+        if (tid == 0) {
+            mbar_wait(&bar_g, phase);
+            tc_fence_after();
+            if (chunk == 0) mbar_wait(&bar_v, 0);
+            const uint32_t g_addr = smem_u32(Gimg), v_addr = smem_u32(smem + L.off_v);
+            // Dots[hit, pix] = G[hit, ch] V[pix, ch]^T     (A: G image K-major; B: V image MN-major)
+            for (int ks = 0; ks < DH / 16; ++ks)
+                umma_f16(tm_dots, umma_desc(g_addr + ks * 256, 128, CG * 128),
+                         umma_desc(v_addr + ks * 2 * G * 128, G * 128, 128), idesc_dots | n_bits, ks > 0 ? 1u : 0u);
+            umma_commit(&bar_dots);
+        }
+        tb.lap(17);                                  // G image stores, Dots MMA issue
         // ---- my hit: softmax over all points (both threads of the pair compute it), then my PPT points
         const int n = n_cur;
         float aw[PPT], ddx[PPT], ddy[PPT], inv_cnt = 0.f;
@@ -297,7 +341,10 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                 const float wya = a * tent(ddy[p]), wyb = a * tent(ddy[p] - 1.f);
                 wa[p] = __floats2half2_rn(wya * wxa, wya * wxb);
                 wb[p] = __floats2half2_rn(wyb * wxa, wyb * wxb);
-                tap_pix[p] = __float_as_int(fmaf(cy, fSw, cx) + pix_bias) - 0x4B000000;
+                const int k = __float_as_int(fmaf(cy, fSw, cx) + pix_bias) - 0x4B000000;
+                tap_pix[p] = k;
+                tap_o01[p] = koffb(k) | (koffb(k + 1) << 16);
+                tap_o23[p] = koffb(k + Sw) | (koffb(k + Sw + 1) << 16);
             }
             tapped = true;
         }
@@ -307,9 +354,8 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             if (n >= 0 && half == round) {
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
-                    const int k = tap_pix[p];
-                    const uint32_t a0 = myrow + koffb(k), a1 = myrow + koffb(k + 1);
-                    const uint32_t a2 = myrow + koffb(k + Sw), a3 = myrow + koffb(k + Sw + 1);
+                    const uint32_t a0 = myrow + (tap_o01[p] & 0xffffu), a1 = myrow + (tap_o01[p] >> 16);
+                    const uint32_t a2 = myrow + (tap_o23[p] & 0xffffu), a3 = myrow + (tap_o23[p] >> 16);
                     const uint16_t h0 = b2_lds16(a0), h1 = b2_lds16(a1), h2 = b2_lds16(a2), h3 = b2_lds16(a3);
                     b2_sts16(a0, __half_as_ushort(__hadd(__ushort_as_half(h0), __low2half(wa[p]))));
                     b2_sts16(a1, __half_as_ushort(__hadd(__ushort_as_half(h1), __high2half(wa[p]))));
@@ -319,28 +365,13 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             }
             __syncwarp();
         }
-        tb.lap(18);                                  // A' rows (+ latency of the G gathers)
-#pragma unroll
-        for (int u = 0; u < kG; ++u) {
-            const int i = tid + u * kB2Threads;
-            if (i < kB2Hits * CG) {
-                const int rr = i / CG, cg = i % CG;
-                *reinterpret_cast<uint4*>(Gimg + ((rr >> 3) * CG + cg) * 64 + (rr & 7) * 8) = g_cur[u];
-            }
-        }
-        tb.lap(17);                                  // G image stores
+        tb.lap(18);                                  // A' rows
         proxy_fence();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            if (chunk == 0) mbar_wait(&bar_v, 0);
-            const uint32_t a_addr = smem_u32(smem + L.off_a), g_addr = smem_u32(Gimg), v_addr = smem_u32(smem + L.off_v);
-            // Dots[hit, pix] = G[hit, ch] V[pix, ch]^T     (A: G image K-major; B: V image MN-major)
-            for (int ks = 0; ks < DH / 16; ++ks)
-                umma_f16(tm_dots, umma_desc(g_addr + ks * 256, 128, CG * 128),
-                         umma_desc(v_addr + ks * 2 * G * 128, G * 128, 128), idesc_dots | n_bits, ks > 0 ? 1u : 0u);
-            umma_commit(&bar_dots);
+            const uint32_t a_addr = smem_u32(smem + L.off_a), g_addr = smem_u32(Gimg);
             // dV^T[ch, pix] += G^T[ch, hit] A'[hit, pix]   (A: G image MN-major; B: A' image MN-major)
             for (int ks = 0; ks < kB2Hits / 16; ++ks)
                 umma_f16(tm_dv, umma_desc(g_addr + ks * 2 * CG * 128, CG * 128, 128),
@@ -348,10 +379,9 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                          (chunk > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&bar_dv);
         }
-        load_g(sn_next, g_nx);                       // next chunk's grad_slots rows: in flight during the read-back
         mbar_wait(&bar_dots, phase);
         tc_fence_after();
-        tb.lap(19);                                  // fences, MMA issue, Dots MMAs
+        tb.lap(19);                                  // fences, dV^T MMA issue, wait for the Dots MMAs
         // ---- Dots: TMEM -> registers -> lane-interleaved staging; warp w reads lane quarter w & 3, column half w >> 2
         {
             const int c_beg = (warp >> 2) ? (SP / 16) * 8 : 0, c_end = (warp >> 2) ? SP : (SP / 16) * 8;
@@ -395,14 +425,25 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         }
         t += __shfl_xor_sync(VER_FULL_MASK, t, 1);               // the other half of my hit's points
         if (n >= 0) {
+            // my PPT attention-logit gradients and 2 PPT offset gradients are contiguous: vector reductions
+            // (d loc = aw * size * sum(...), d offset = d loc / size  -> the size cancels)
             float* grow = glogits + ((size_t)b * Nq + n) * ld;
+            float gw[PPT], go[2 * PPT];
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
-                const int pp = half * PPT + p;
-                atomicAdd(grow + NH * NP * 2 + h * NP + pp, aw[p] * (ga[p] - t));
-                // d loc = aw * size * sum(...), d offset = d loc / size  -> the size cancels
-                atomicAdd(grow + h * NP * 2 + 2 * pp, inv_cnt * aw[p] * gx[p]);
-                atomicAdd(grow + h * NP * 2 + 2 * pp + 1, inv_cnt * aw[p] * gy[p]);
+                gw[p] = aw[p] * (ga[p] - t);
+                go[2 * p] = inv_cnt * aw[p] * gx[p];
+                go[2 * p + 1] = inv_cnt * aw[p] * gy[p];
+            }
+            float* dw = grow + NH * NP * 2 + h * NP + half * PPT;
+            float* dof = grow + h * NP * 2 + half * PPT * 2;
+            if (PPT == 4) {
+                red_add_v4(dw, gw[0], gw[1], gw[2], gw[3]);
+                red_add_v4(dof, go[0], go[1], go[2], go[3]);
+                red_add_v4(dof + 4, go[4], go[5], go[6], go[7]);
+            } else {
+                red_add_v2(dw, gw[0], gw[1]);
+                red_add_v4(dof, go[0], go[1], go[2], go[3]);
             }
         }
         tb.lap(21);                                  // tap read-back, softmax backward, atomics
@@ -413,8 +454,6 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         n_cur = n_nx;
         n_nx = n_n2;
         d_cur = d_nx;
-#pragma unroll
-        for (int u = 0; u < kG; ++u) g_cur[u] = g_nx[u];
         tb.lap(23);                                  // wait: dV^T MMAs retired
     }
     // ---- grad_value: dV^T (TMEM lanes = channel) -> [bv][pix][h][ch] fp32

@@ -232,10 +232,16 @@ sca_fwd_tc4_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                     uint32_t km = s_kmask[g][par][0] | s_kmask[g][par][1] | s_kmask[g][par][2] | s_kmask[g][par][3];
                     uint32_t acc = first_cam ? 0u : 1u;
                     if (!acc && !km) km = 1u;          // (an all-zero chunk zeroes the accumulator)
-                    for (; km; km &= km - 1) {
-                        const int ks = __ffs(km) - 1;
-                        umma_f16_ts(tmem + g * DH, a_addr + ks * 8, umma_desc(v_addr + ks * 256, 128, G * 128), idesc, acc);
-                        acc = 1u;
+                    // straight-line issue: one descriptor per batch, compile-time increments per K chunk (a
+                    // find-first-set loop that rebuilds the descriptor costs ~150 cycles per MMA on the uniform datapath)
+                    const uint64_t dv0 = umma_desc(v_addr, 128, G * 128);
+                    const uint32_t d_addr = tmem + g * DH;
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks) {
+                        if ((km >> ks) & 1u) {
+                            umma_f16_ts(d_addr, a_addr + ks * 8, dv0 + (uint64_t)(ks * 16), idesc, acc);
+                            acc = 1u;
+                        }
                     }
                     umma_commit(&bar_mma[g]);
                     if (last_cam) {

@@ -445,13 +445,45 @@ def value_image(value, NH):
     return vimg
 
 
+def value_image16(value, NH, Sh, Sw):
+    """fp16 value maps (Bv, Sh*Sw, C) -> operand images with 16-cell image rows (Bv, NH, Dh/8, 2*Sh, 8, 8):
+    cell y*16 + x + 1 holds pixel (y, x), the rest of an image row is zero (sca_fwd_tc6_kernel's layout)."""
+    _need_cuda(value)
+    assert value.dtype == torch.float16
+    value = _c(value)
+    Bv, S = value.shape[:2]
+    assert S == Sh * Sw
+    Dh = value[0].numel() // S // NH
+    vimg = torch.empty((Bv, NH, Dh // 8, 2 * Sh, 8, 8), dtype=torch.float16, device=value.device)
+    check(lib.ver_value_image16_f16(_ptr(value), _ptr(vimg), Bv, Sh, Sw, NH, Dh, _stream()))
+    return vimg
+
+
+def sca_forward_sorted16(vimg16, logits, vis, Sh, Sw, NH, NP):
+    """Forward sampler on 16-cell image rows (sca_fwd_tc6_kernel): slots (B, Nq, C) fp16."""
+    _need_cuda(vimg16, logits)
+    Ncam, B = vis.rpc.shape[:2]
+    Z, H, W = vis.grid
+    Nq = Z * H * W
+    Dh = vimg16.shape[2] * 8
+    if not lib.ver_tc6_supported(Ncam, Sh, Sw, Dh, NP):
+        raise VerError('sca_forward_sorted16: shape not covered (Ncam <= 32, Sh, Sw <= 14, Dh in 32/64/96, NP in 4/8)')
+    order, smask, tile_union = vis.order
+    slots = torch.empty((B, Nq, NH * Dh), dtype=torch.float16, device=logits.device)
+    check(lib.ver_sca_forward_sorted16(_ptr(vimg16), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
+                                       _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw, NH, Dh, NP,
+                                       _stream()))
+    return slots
+
+
 VER_LAYOUT_TC_IMAGE = 2
 # 'sorted': visibility-sorted rows, the fastest measured kernel generation that covers the shape
 # (sca_fwd_tc4_kernel); 'sorted3' / 'sorted4' / 'sorted5': force a generation (tests and tools/ A-B timing only;
 # sorted5 = sca_fwd_tc5_kernel: three A operands in TMEM, two issuing threads, bounded waits);
-# 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
+# 'sorted16': sca_fwd_tc6_kernel on 16-cell image rows (two builder threads per row, A in the shared-memory operand;
+# measured slower than sorted4, kept as an experiment with its parity test); 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
 TC_FORWARD = 'sorted'
-_SORTED_VARIANT = {'sorted': 0, 'sorted3': 3, 'sorted4': 4, 'sorted5': 5}
+_SORTED_VARIANT = {'sorted': 0, 'sorted3': 3, 'sorted4': 4, 'sorted5': 5, 'sorted16': 0}
 
 
 class SCASampleTCFunction(Function):
@@ -477,7 +509,9 @@ class SCASampleTCFunction(Function):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if TC_FORWARD in _SORTED_VARIANT and NP % 4 == 0 and logits.shape[1] % 4 == 0:
+        if (TC_FORWARD == 'sorted16' and logits.shape[1] % 4 == 0 and lib.ver_tc6_supported(Ncam, Sh, Sw, Dh, NP)):
+            slots = sca_forward_sorted16(value_image16(value, NH, Sh, Sw), logits, vis, Sh, Sw, NH, NP)
+        elif TC_FORWARD in _SORTED_VARIANT and NP % 4 == 0 and logits.shape[1] % 4 == 0:
             order, smask, tile_union = vis.order
             check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
                                              _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw,
