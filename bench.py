@@ -34,6 +34,11 @@ NCAM = 18
 PER_GPU_BATCH = 8
 EMBED = 768
 LOSS_SCALE = 1024.0
+# multi-GPU: size of the gradient buckets reduced on a side stream while the backward pass is still running; 0 (default)
+# = ONE all-reduce after backward.  Measured on 2 x B200 (profiles/r02q_*): one exposed all-reduce 21.36 ms per step
+# (N = 1: 20.94), 8 MB buckets overlapped with backward 21.69 ms -- the NCCL kernels running next to the GEMMs cost
+# more than the 0.4 ms they hide, so the overlap stays off.
+BUCKET_BYTES = int(os.environ.get('VER_BUCKET_BYTES', 0))
 METRIC = 'panoramas/sec (18-view->voxel lift+encode, fwd+bwd+optimizer step)'
 # BASELINE.json configs 3 and 5 (the headline line is config 2): (name, mode, batch/GPU, grid Z H W)
 SWEEP = [('config3 get_occ.py inference', 'infer', 64, (16, 40, 40)),
@@ -214,7 +219,9 @@ class Config:
                 # graphed multi-GPU step: the one exchange of SURVEY 8(e) as ONE captured NCCL all-reduce over a
                 # flat gradient buffer (torch DDP's reducer hooks cannot be carried through a capture)
                 from vln_ver_b200.dist_utils import FlatGradients
-                self.bucket = FlatGradients(self.params)
+                # buckets of ~8 MB reduced on a side stream as soon as their gradients are complete (captured as graph
+                # edges): only the bucket that is ready last (the query embedding, 79 MB) stays exposed
+                self.bucket = FlatGradients(self.params, bucket_bytes=BUCKET_BYTES, overlap=BUCKET_BYTES > 0)
             elif self.ddp:
                 self.wrap_ddp()
             # vocc.py:261-268; capturable: the step counter lives on the device (CUDA-graph replay)
@@ -233,6 +240,7 @@ class Config:
     def wrap_ddp(self):
         """eager multi-GPU step: torch DDP (bucketed all-reduce overlapped with backward)."""
         if self.bucket is not None:
+            self.bucket.close()
             self.bucket = None
             for p in self.params:
                 p.grad = None
@@ -265,8 +273,12 @@ class Config:
         from vln_ver_b200.graph import CapturedStep
         try:
             self.captured = CapturedStep(self.step, self.pool_dev[0], warmup=warmup, ddp=self.ddp and self.train)
-            self.graph_note = 'cuda graph replay' + (' (gradient all-reduce captured in the graph)'
-                                                     if self.bucket is not None else '')
+            self.graph_note = 'cuda graph replay'
+            if self.bucket is not None:
+                nb = len(self.bucket.buckets)
+                self.graph_note += (f' (gradient all-reduce captured in the graph: {nb} buckets, reduced on a side '
+                                    f'stream while backward runs)' if self.bucket.overlap else
+                                    ' (gradient all-reduce captured in the graph)')
         except Exception as e:  # noqa: BLE001  (fall back to eager, say why)
             self.captured = None
             self.graph_note = f'eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})'

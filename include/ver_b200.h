@@ -295,6 +295,8 @@ int ver_cast_colsum(int dtype, const float* x, void* y, int64_t rows, int C, flo
  * LAST word is a counter that must be zero on entry (the kernel leaves it zero); one launch per scratch at a time. */
 int ver_colsum_fold_scratch_floats(int C);
 int ver_colsum_fold(const float* part, int64_t P, int C, float* out, float* scratch, ver_stream_t stream);
+/* the same for n_mat matrices at once: part [n_mat, P, C] -> out [n_mat, C] (one launch; scratch-free) */
+int ver_colsum_fold_batched(const float* part, int n_mat, int64_t P, int C, float* out, ver_stream_t stream);
 /* Column sums of an fp16 matrix x[rows, C] as partial sums (layout as above): the bias gradient of a Linear whose
  * output gradient is already fp16 (the occupancy head's occ_proj / occ_branches, HEAD:236-248). */
 int ver_colsum_f16(const void* x, int64_t rows, int C, float* colsum_part, ver_stream_t stream);

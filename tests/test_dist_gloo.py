@@ -47,6 +47,7 @@ def _worker(rank, world, port, out):
     loss = _loss(sd, head, feats[:, lo:hi].double(), l2i[lo:hi], sh[lo:hi], gts[lo:hi])
     loss.backward()
     names = [k for k, v in sd.items() if v.grad is not None]
+    local = {k: sd[k].grad.detach().float().clone() for k in names}      # this rank's gradient, before any exchange
     # the flat bucket of the graphed step (fp32 master gradients as views into one buffer, one collective)
     p32 = [torch.nn.Parameter(sd[k].detach().float()) for k in names]
     bucket = dist_utils.FlatGradients(p32)
@@ -58,6 +59,19 @@ def _worker(rank, world, port, out):
     dist_utils.allreduce_mean_([sd[k].grad for k in names])
     for p, k in zip(p32, names):                  # same mean through both paths (fp32 vs fp64)
         assert flat_ok and torch.allclose(p.grad.double(), sd[k].grad, rtol=1e-5, atol=1e-7), k
+    # the bucketed, overlapped form of the same exchange: every bucket is reduced from autograd's post-accumulate
+    # hooks as soon as its last gradient has arrived (bench.py's multi-GPU step); same mean
+    q32 = [torch.nn.Parameter(sd[k].detach().float()) for k in names]
+    over = dist_utils.FlatGradients(q32, bucket_bytes=4096, overlap=True)
+    assert over.overlap and len(over.buckets) > 2 and over.buckets[0][0] == 0 and over.buckets[-1][1] == over.flat.numel()
+    for _ in range(2):                            # twice: the per-step bookkeeping resets
+        over.zero_()
+        sum((q * local[k]).sum() for q, k in zip(q32, names)).backward()     # d/dq = this rank's gradient
+        assert any(over.launched)                 # hooks fired during backward
+        over.allreduce_mean_()
+        assert not any(over.launched) and over.pending == [n for _, _, n in over.buckets]
+        for q, p in zip(q32, p32):
+            assert torch.allclose(q.grad, p.grad, rtol=1e-6, atol=1e-8)
     ms = dist_utils.max_over_ranks(10.0 + rank)
     if rank == 0:
         torch.save({'grads': {k: sd[k].grad for k in names}, 'ms': ms}, out)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round-2 visit: full parity suite, smoke, bench (default line), then the ncu evidence of profile_step.sh.
+tag=${1:-run}
+out=gpurun_out/$tag
+mkdir -p $out
+timeout 420 python -m pytest tests -m gpu -q -x > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
+timeout 120 python __graft_entry__.py smoke > $out/smoke.log 2>&1; echo "smoke exit $?" >> $out/smoke.log
+timeout 400 python bench.py --steps 20 --warmup 3 > $out/bench.json 2> $out/bench.err; echo "bench exit $?" >> $out/bench.err
+tail -4 $out/pytest.log; tail -2 $out/smoke.log; cat $out/bench.json; tail -1 $out/bench.err
+if [ "${2:-}" = "prof" ]; then bash tools/profile_step.sh $tag; fi

@@ -5,6 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vln_ver_b200 import fused_layer as F, ops
 from vln_ver_b200._lib import VER_F16, check, lib
 
+import ctypes
+lib.ver_debug_ln_bwd_tma.restype = ctypes.c_int
+lib.ver_debug_ln_bwd_tma.argtypes = [ctypes.c_int]
 R, C, FF = 204800, 768, 1536
 dev = 'cuda'
 g = torch.Generator(device=dev).manual_seed(0)
@@ -34,10 +37,17 @@ for p in (0.0, 0.1):
     y, z, st = F._ln_fwd(x, res, gam, bet, p, 1e-5, 1234, True)
     t = timeit(lambda: F._ln_fwd(x, res, gam, bet, p, 1e-5, 1234, True))
     print(f'dropout_add_ln_fwd p={p}: {t:.1f} us  ({4 * R * C * 2 / t / 1e3:.0f} GB/s incl. allocation of outputs)')
-    t = timeit(lambda: F._ln_bwd(dy, z, st, gam, p, 1234))
-    print(f'dropout_add_ln_bwd p={p}: {t:.1f} us  ({4 * R * C * 2 / t / 1e3:.0f} GB/s incl. partial sums)')
+    outs = {}
+    for tma in (1, 0):
+        lib.ver_debug_ln_bwd_tma(tma)
+        outs[tma] = F._ln_bwd(dy, z, st, gam, p, 1234)
+        t = timeit(lambda: F._ln_bwd(dy, z, st, gam, p, 1234))
+        print(f'dropout_add_ln_bwd p={p} {"TMA ring" if tma else "register loads"}: {t:.1f} us  '
+              f'({4 * R * C * 2 / t / 1e3:.0f} GB/s incl. partial sums + fold)')
+    lib.ver_debug_ln_bwd_tma(1)
+    print('  TMA-fed == register-fed:', all(torch.equal(a, b) for a, b in zip(outs[1], outs[0])))
     hh = h.clone()
-    t = timeit(lambda: check(lib.ver_relu_dropout_fwd(VER_F16, hh.data_ptr(), hh.data_ptr(), hh.numel(), p, 99,
+    t = timeit(lambda: check(lib.ver_relu_dropout_fwd(VER_F16, hh.data_ptr(), hh.data_ptr(), hh.numel(), p, 99, None,
                                                       torch.cuda.current_stream().cuda_stream)))
     print(f'relu_dropout_fwd p={p}: {t:.1f} us  ({2 * R * FF * 2 / t / 1e3:.0f} GB/s)')
     d2 = dh.clone()

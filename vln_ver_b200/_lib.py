@@ -76,6 +76,7 @@ def _load():
         'ver_colsum_f16': (c_int, [P, c_int64, c_int, P, P]),
         'ver_colsum_fold_scratch_floats': (c_int, [c_int]),
         'ver_colsum_fold': (c_int, [P, c_int64, c_int, P, P, P]),
+        'ver_colsum_fold_batched': (c_int, [P, c_int, c_int64, c_int, P, P]),
         'ver_focal_loss': (c_int, [P, P, c_int, P, P, P, P, c_int64, c_int, c_float, c_float, P]),
         'ver_occupancy_decode': (c_int, [P, c_int64, c_int, c_float, P, P, P, P]),
     }

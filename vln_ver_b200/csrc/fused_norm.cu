@@ -279,6 +279,159 @@ dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const floa
     if (dxsum_part) reduce(ds, dxsum_part);
 }
 
+// ---------------------------------------------------------------- backward, rows fed by the TMA engine (fp16)
+// Same arithmetic as dropout_add_ln_bwd.  What changed: the dy / z rows reach the warp through a ring of kLnStages
+// shared-memory row slots filled by cp.async.bulk (one elected lane, completion on an mbarrier per slot) instead of
+// register loads.  The register version keeps 72 column accumulators per thread and therefore runs 16 warps per SM
+// with 3 KB in flight each (49 KB per SM: 4.0 TB/s, profiles/r02n); the ring keeps kLnStages rows of both tensors
+// in flight per warp without costing a register, and the second pass re-reads shared memory instead of holding the
+// packed rows in 24 registers.
+constexpr int kLnStages = 4;
+template <int NV>
+__global__ void __launch_bounds__(256, 2)
+dropout_add_ln_bwd_tma(const __half* __restrict__ dy, const __half* __restrict__ z, const float2* __restrict__ stats,
+                       const float* __restrict__ gamma, __half* __restrict__ dx, __half* __restrict__ dres,
+                       float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, float* __restrict__ dxsum_part,
+                       int64_t rows, int C, float p, uint64_t seed, const unsigned long long* __restrict__ seed_epoch) {
+    if (seed_epoch) seed += *seed_epoch;
+    // [8 warps][kLnStages][dy row | z row]; the first 8 * C floats double as the reduction buffer at the end
+    extern __shared__ __align__(128) unsigned char s_ring[];
+    __shared__ __align__(8) uint64_t s_full[8][kLnStages];
+    __shared__ float4 s_g[2][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t row_bytes = (uint32_t)C * 2u;
+    unsigned char* my_ring = s_ring + (size_t)warp * kLnStages * 2 * row_bytes;
+    const uint32_t thr16 = (uint32_t)(p * 65536.f);
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    float dg[NV][8], db[NV][8], ds[NV][8];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dg[k][e] = db[k][e] = ds[k][e] = 0.f;
+    for (int i = threadIdx.x; i < C / 8; i += blockDim.x) {
+        s_g[0][i] = reinterpret_cast<const float4*>(gamma)[2 * i];
+        s_g[1][i] = reinterpret_cast<const float4*>(gamma)[2 * i + 1];
+    }
+    if (lane == 0) {
+        for (int st = 0; st < kLnStages; ++st) mbar_init(&s_full[warp][st], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto load_gamma = [&](int c, float (&gm)[8]) {
+        const float4 a = s_g[0][c >> 3], b = s_g[1][c >> 3];
+        gm[0] = a.x; gm[1] = a.y; gm[2] = a.z; gm[3] = a.w; gm[4] = b.x; gm[5] = b.y; gm[6] = b.z; gm[7] = b.w;
+    };
+    const int64_t row0 = (int64_t)blockIdx.x * kRowsPerBlock + warp, stride = (int64_t)gridDim.x * kRowsPerBlock;
+    auto issue = [&](int64_t it) {                      // row of iteration `it` -> slot it % kLnStages (lane 0)
+        const int64_t row = row0 + it * stride;
+        if (row >= rows) return;
+        const int st = (int)(it % kLnStages);
+        unsigned char* slot = my_ring + (size_t)st * 2 * row_bytes;
+        mbar_expect_tx(&s_full[warp][st], 2 * row_bytes);
+        bulk_g2s(slot, dy + row * C, row_bytes, &s_full[warp][st]);
+        bulk_g2s(slot + row_bytes, z + row * C, row_bytes, &s_full[warp][st]);
+    };
+    if (lane == 0)
+        for (int it = 0; it < kLnStages; ++it) issue(it);
+    int64_t it = 0;
+    for (int64_t row = row0; row < rows; row += stride, ++it) {
+        const int st = (int)(it % kLnStages);
+        const float2 stt = stats[row];
+        mbar_wait(&s_full[warp][st], (uint32_t)((it / kLnStages) & 1));
+        const unsigned char* slot = my_ring + (size_t)st * 2 * row_bytes;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+                Vec8<__half> vy, vz;
+                vy.load(reinterpret_cast<const __half*>(slot) + c);
+                vz.load(reinterpret_cast<const __half*>(slot + row_bytes) + c);
+                float fy[8], fz[8], gm[8];
+                vy.get(fy);
+                vz.get(fz);
+                load_gamma(c, gm);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (fz[e] - stt.x) * stt.y, g = fy[e] * gm[e];
+                    s1 += g;
+                    s2 += g * xh;
+                    dg[k][e] += fy[e] * xh;
+                    db[k][e] += fy[e];
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            s1 += __shfl_xor_sync(VER_FULL_MASK, s1, o);
+            s2 += __shfl_xor_sync(VER_FULL_MASK, s2, o);
+        }
+        const float m1 = s1 / (float)C, m2 = s2 / (float)C;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+                Vec8<__half> vy, vz;
+                vy.load(reinterpret_cast<const __half*>(slot) + c);
+                vz.load(reinterpret_cast<const __half*>(slot + row_bytes) + c);
+                float fy[8], fz[8], dz[8], gm[8];
+                vy.get(fy);
+                vz.get(fz);
+                load_gamma(c, gm);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (fz[e] - stt.x) * stt.y;
+                    dz[e] = stt.y * (fy[e] * gm[e] - m1 - xh * m2);
+                }
+                Vec8<__half> o;
+                if (dres) {
+                    o.set(dz);
+                    o.store(dres + row * C + c);
+                }
+                if (p > 0.f) {
+                    const uint32_t m = keep8((uint64_t)row * C + c, seed, thr16);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dz[e] = ((m >> e) & 1) ? dz[e] * scale : 0.f;
+                }
+                o.set(dz);
+                o.store(dx + row * C + c);
+                if (dxsum_part) {          // what was stored (rounded to fp16) is what the bias gradient sums
+                    o.get(dz);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) ds[k][e] += dz[e];
+                }
+            }
+        }
+        __syncwarp();                                   // every lane is done with the slot: refill it
+        if (lane == 0) issue(it + kLnStages);
+    }
+    // block-level reduction of the parameter-gradient partials through [8][C] floats (the ring is idle now: every
+    // issued copy has been waited for)
+    __syncthreads();
+    float* s_part = reinterpret_cast<float*>(s_ring);
+    auto reduce = [&](float (&acc)[NV][8], float* out) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            if (c < C) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s_part[warp * C + c + e] = acc[k][e];
+            }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += s_part[w * C + c];
+            out[(size_t)blockIdx.x * C + c] = a;
+        }
+        __syncthreads();
+    };
+    reduce(dg, dgamma_part);
+    reduce(db, dbeta_part);
+    if (dxsum_part) reduce(ds, dxsum_part);
+}
+
 // ---------------------------------------------------------------- h = dropout(relu(a)), in place capable
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -419,6 +572,13 @@ extern "C" int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const voi
 
 extern "C" int ver_dropout_add_layernorm_bwd_blocks(int64_t rows) { return ln_grid(rows); }
 
+// A/B switch of tools/ln_bench.py and the tests: 1 (default) = TMA-fed fp16 backward where it applies, 0 = register loads
+static int g_ln_bwd_tma = 1;
+extern "C" int ver_debug_ln_bwd_tma(int on) {
+    g_ln_bwd_tma = on;
+    return VER_OK;
+}
+
 extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const void* z, const float* stats,
                                              const float* gamma, void* dx, void* dresidual,
                                              float* dgamma_part, float* dbeta_part, float* dxsum_part,
@@ -432,7 +592,20 @@ extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const vo
     const int nv = (C + 255) / 256;
     const int grid = ln_grid(rows);
     const size_t smem = (size_t)8 * C * sizeof(float);
-    if (dtype == VER_F16) {
+    // fp16 rows of a whole number of 16-byte units, ring + partials within half an SM's shared memory: TMA-fed kernel
+    const size_t ring = (size_t)8 * kLnStages * 2 * C * 2;
+    if (dtype == VER_F16 && g_ln_bwd_tma && ring >= smem && ring <= 100 * 1024) {
+        cudaFuncSetAttribute(dropout_add_ln_bwd_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+        cudaFuncSetAttribute(dropout_add_ln_bwd_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+        cudaFuncSetAttribute(dropout_add_ln_bwd_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+        cudaFuncSetAttribute(dropout_add_ln_bwd_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+#define LN_TMA(NVV) dropout_add_ln_bwd_tma<NVV><<<grid, 256, ring, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep)
+        if (nv <= 1) LN_TMA(1);
+        else if (nv <= 2) LN_TMA(2);
+        else if (nv <= 3) LN_TMA(3);
+        else LN_TMA(4);
+#undef LN_TMA
+    } else if (dtype == VER_F16) {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -486,54 +659,62 @@ extern "C" int ver_relu_dropout_bwd(int dtype, const void* dh, const void* h, vo
     return VER_OK;
 }
 
-// ---------------------------------------------------------------- out[C] = sum over the P rows of part[P, C]
+// ---------------------------------------------------------------- out[m, C] = sum over the P rows of part[m, P, C]
 // Folds the partial sums the kernels above emit (per-thread 8-float groups viewed as rows of C floats, or per-block
-// rows).  Two levels in one launch, deterministic: every block reduces its slice of rows into block_part[b][C], the
-// block that finishes last (threadfence + counter) adds the block partials in a fixed order.  Replaces a torch
-// reduction that took 30 us per call (57 calls per training step) because its output has only C elements.
-constexpr int kFoldBlocks = 296;
-__global__ void __launch_bounds__(256)
-colsum_fold_kernel(const float* __restrict__ part, int64_t P, int C, float* __restrict__ out,
-                   float* __restrict__ block_part, unsigned int* __restrict__ counter) {
-    const int nb = gridDim.x;
-    const int64_t per = (P + nb - 1) / nb, r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < P ? r0 + per : P;
-    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int64_t r = r0; r < r1; ++r) {
-            const float4 v = *reinterpret_cast<const float4*>(part + r * C + c);
+// rows).  One block of 32 warps per 128-column slab and matrix: warp w adds rows w, w + 32, ... (coalesced 512-byte
+// row segments, four independent loads in flight per lane), the 32 warp partials are added in a fixed order --
+// deterministic, one pass over the data.  (Round-2 profile r02n: the previous version let the LAST block add 296
+// block partials serially -- 54 us per call, 31 calls per step = 1.7 ms of a 21 ms step for a few megabytes.)
+__global__ void __launch_bounds__(1024)
+colsum_fold_kernel(const float* __restrict__ part, int64_t P, int C, float* __restrict__ out) {
+    __shared__ float4 s_acc[32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + lane * 4;
+    const float* src = part + (size_t)blockIdx.y * P * C + c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+        int64_t r = warp;
+        for (; r + 96 < P; r += 128) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + r * C));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (r + 32) * C));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(src + (r + 64) * C));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(src + (r + 96) * C));
+            a.x += (v0.x + v1.x) + (v2.x + v3.x);
+            a.y += (v0.y + v1.y) + (v2.y + v3.y);
+            a.z += (v0.z + v1.z) + (v2.z + v3.z);
+            a.w += (v0.w + v1.w) + (v2.w + v3.w);
+        }
+        for (; r < P; r += 32) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * C));
             a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         }
-        *reinterpret_cast<float4*>(block_part + (size_t)blockIdx.x * C + c) = a;
     }
-    __shared__ bool last;
-    __threadfence();
+    s_acc[warp][lane] = a;
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == (unsigned int)nb - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int b = 0; b < nb; ++b) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(block_part + (size_t)b * C + c));
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    if (warp == 0 && c < C) {
+        float4 t = s_acc[0][lane];
+#pragma unroll
+        for (int w = 1; w < 32; ++w) {
+            const float4 v = s_acc[w][lane];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
-        *reinterpret_cast<float4*>(out + c) = a;
+        *reinterpret_cast<float4*>(out + (size_t)blockIdx.y * C + c) = t;
     }
-    if (threadIdx.x == 0) *counter = 0;           // ready for the next launch on this stream
 }
 
-extern "C" int ver_colsum_fold_scratch_floats(int C) { return kFoldBlocks * C + 4; }
+extern "C" int ver_colsum_fold_scratch_floats(int C) { return 4; }     // (kept for ABI stability: no scratch needed)
 
-extern "C" int ver_colsum_fold(const float* part, int64_t P, int C, float* out, float* scratch, ver_stream_t stream) {
-    VER_CHECK_ARG(part && out && scratch && P > 0 && C > 0 && C % 4 == 0, "bad arguments");
-    // scratch: [kFoldBlocks * C] block partials + one counter word that must be ZERO on entry (the kernel resets it)
-    const int nb = (int)(P < kFoldBlocks ? P : kFoldBlocks);
-    colsum_fold_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(part, P, C, out, scratch,
-                                                             reinterpret_cast<unsigned int*>(scratch + (size_t)kFoldBlocks * C));
+extern "C" int ver_colsum_fold_batched(const float* part, int n_mat, int64_t P, int C, float* out, ver_stream_t stream) {
+    VER_CHECK_ARG(part && out && n_mat > 0 && P > 0 && C > 0 && C % 4 == 0, "bad arguments");
+    colsum_fold_kernel<<<dim3((C + 127) / 128, n_mat), 1024, 0, (cudaStream_t)stream>>>(part, P, C, out);
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;
+}
+
+extern "C" int ver_colsum_fold(const float* part, int64_t P, int C, float* out, float* scratch, ver_stream_t stream) {
+    (void)scratch;
+    return ver_colsum_fold_batched(part, 1, P, C, out, stream);
 }
 
 extern "C" int ver_colsum_f16(const void* x, int64_t rows, int C, float* colsum_part, ver_stream_t stream) {

@@ -108,26 +108,25 @@ def _ln_bwd(dy, z, stats, gamma32, p, seed):
     check(lib.ver_dropout_add_layernorm_bwd(VER_F16, _ptr(dy), _ptr(z), _ptr(stats), _ptr(gamma32), _ptr(dx),
                                             _ptr(dres), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), rows, C,
                                             float(p), seed, _ptr(ops._seed_epoch(z.device)), _stream()))
-    return dx, dres, _fold_rows(part[0]), _fold_rows(part[1]), _fold_rows(part[2])
+    folded = _fold_mats(part)                       # dgamma, dbeta, colsum(dx) in one launch
+    return dx, dres, folded[0], folded[1], folded[2]
 
 
 def _colsum_part(device):
     return torch.empty((lib.ver_colsum_partial_rows(), 8), dtype=torch.float32, device=device)
 
 
-_FOLD_SCRATCH = {}
-
-
 def _fold_rows(part2d):
-    """(P, C) fp32 partial sums -> (C,): ver_colsum_fold (one deterministic two-level launch)."""
-    P, C = part2d.shape
-    key = (part2d.device.index, C)
-    scratch = _FOLD_SCRATCH.get(key)
-    if scratch is None:      # zeroed once: the kernel leaves the counter word zero
-        scratch = _FOLD_SCRATCH[key] = torch.zeros(lib.ver_colsum_fold_scratch_floats(C), dtype=torch.float32,
-                                                   device=part2d.device)
-    out = torch.empty(C, dtype=torch.float32, device=part2d.device)
-    check(lib.ver_colsum_fold(_ptr(part2d), P, C, _ptr(out), _ptr(scratch), _stream()))
+    """(P, C) fp32 partial sums -> (C,): ver_colsum_fold_batched (one deterministic launch)."""
+    return _fold_mats(part2d[None])[0]
+
+
+def _fold_mats(part3d):
+    """(m, P, C) fp32 partial sums -> (m, C) in one launch."""
+    m, P, C = part3d.shape
+    assert part3d.is_contiguous()
+    out = torch.empty((m, C), dtype=torch.float32, device=part3d.device)
+    check(lib.ver_colsum_fold_batched(_ptr(part3d), m, P, C, _ptr(out), _stream()))
     return out
 
 
