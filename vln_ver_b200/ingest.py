@@ -21,37 +21,72 @@ class DevicePrefetcher:
         for batch in DevicePrefetcher(host_batches, device):
             outs = head(batch['feats'], None, lidar2img=batch['l2i'], originshift=batch['sh'])
 
-    Every batch is copied exactly once; nothing is copied beyond the last batch of `host_batches`."""
+    Every batch is copied exactly once; nothing is copied beyond the last batch of `host_batches`.  Batches of the same
+    shapes land in TWO device buffer sets used alternately (no allocation inside the loop: an allocation on the copy
+    stream can end in cudaMalloc / cudaFree, which synchronise the device); a yielded batch is valid until the
+    next-but-one batch is requested.  `reuse_buffers=False` gives every batch fresh tensors instead."""
 
-    def __init__(self, host_batches, device):
+    def __init__(self, host_batches, device, reuse_buffers=True):
         self.host_batches = host_batches
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise ValueError('DevicePrefetcher copies to a CUDA device')
         self.stream = torch.cuda.Stream(self.device)
         self.h2d_bytes = 0
+        self.reuse = reuse_buffers
+        self._sets = [None, None]            # device buffer sets
+        self._done = [None, None]            # event on the compute stream: the consumer of the set's last batch ran
+        self._n = 0
+
+    def _buffers(self, k, hb):
+        cur = self._sets[k]
+        if cur is not None and cur.keys() == hb.keys() and all(
+                cur[n].shape == v.shape and cur[n].dtype == v.dtype for n, v in hb.items()):
+            return cur
+        self._sets[k] = {n: torch.empty(v.shape, dtype=v.dtype, device=self.device) for n, v in hb.items()}
+        self._done[k] = None
+        return self._sets[k]
 
     def _start(self, hb):
-        with torch.cuda.stream(self.stream):
-            db = {k: v.to(self.device, non_blocking=True) for k, v in hb.items()}
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
+        k = self._n & 1
+        self._n += 1
+        if self.reuse:
+            db = self._buffers(k, hb)                       # (allocated on the current stream, before the copy)
+            if self._done[k] is not None:
+                self.stream.wait_event(self._done[k])       # the previous contents have been consumed
+            else:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                for n, v in hb.items():
+                    db[n].copy_(v, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+        else:
+            with torch.cuda.stream(self.stream):
+                db = {n: v.to(self.device, non_blocking=True) for n, v in hb.items()}
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
         self.h2d_bytes += sum(v.numel() * v.element_size() for v in hb.values())
-        return db, ev
+        return db, ev, k
 
     def __iter__(self):
         it = iter(self.host_batches)
         nxt = next(it, None)
         pending = self._start(nxt) if nxt is not None else None
         while pending is not None:
-            db, ev = pending
+            db, ev, k = pending
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
-            for t in db.values():
-                t.record_stream(cur)              # allocated on the copy stream, consumed on the compute stream
+            if not self.reuse:
+                for t in db.values():
+                    t.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
             nxt = next(it, None)
             pending = self._start(nxt) if nxt is not None else None
             yield db
+            if self.reuse:                        # everything the consumer enqueued on its stream precedes this event
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(self.device))
+                self._done[k] = done
 
 
 # --------------------------------------------------------------------------- file formats either side of the path
