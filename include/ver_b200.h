@@ -248,6 +248,17 @@ int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const void* z, cons
                                   const float* gamma, void* dx, void* dresidual, float* dgamma_part,
                                   float* dbeta_part, float* dxsum_part, int64_t rows, int C, float p_drop,
                                   uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream);
+/* The same pair with the forward's dropout keep bits handed to the backward instead of regenerated there
+ * (one byte per 8 consecutive elements, bit e = element e kept: rows * C / 8 bytes; 1.6 % of one fp16 tensor).
+ * keep_bits may be NULL: forward then stores nothing, backward regenerates the mask from (seed, element index). */
+int ver_dropout_add_layernorm_fwd_bits(int dtype, const void* x, const void* residual, const float* gamma,
+                                       const float* beta, void* y, void* z_out, float* stats, uint8_t* keep_bits,
+                                       int64_t rows, int C, float eps, float p_drop, uint64_t seed,
+                                       const uint64_t* seed_epoch, ver_stream_t stream);
+int ver_dropout_add_layernorm_bwd_bits(int dtype, const void* dy, const void* z, const float* stats,
+                                       const float* gamma, const uint8_t* keep_bits, void* dx, void* dresidual,
+                                       float* dgamma_part, float* dbeta_part, float* dxsum_part, int64_t rows, int C,
+                                       float p_drop, uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream);
 /* ---------------------------------------------------------------- K5: the dense projections
  * nn.Linear as a hand-written tcgen05 GEMM with a fused epilogue (csrc/gemm_tc.cu):
  *     out[M, N] = epilogue(a[M, K] @ w[N, K]^T + bias[N])

@@ -801,13 +801,17 @@ def test_layernorm_backward_column_sums(C, p):
     dy = torch.randn(rows, C, device=DEV, generator=g).half()
     gam = torch.rand(C, device=DEV, generator=g) + 0.5
     bet = torch.randn(C, device=DEV, generator=g)
-    y, z, st = F._ln_fwd(x, res, gam, bet, p, 1e-5, 77, True)
-    dx, dres, dgam, dbet, dxs = F._ln_bwd(dy, z, st, gam, p, 77)
+    y, z, st, bits = F._ln_fwd(x, res, gam, bet, p, 1e-5, 77, True)
+    dx, dres, dgam, dbet, dxs = F._ln_bwd(dy, z, st, gam, p, 77, bits)
     assert rel_err(dxs, dx.float().sum(0)) < 1e-5
+    # the stored keep bits are the regenerated mask: both forms of the backward agree bit for bit
+    assert (bits is None) == (p == 0)
+    again = F._ln_bwd(dy, z, st, gam, p, 77, None)
+    assert all(torch.equal(a, b) for a, b in zip((dx, dres, dgam, dbet, dxs), again))
     # against torch autograd on the same (fp16-rounded) inputs, the mask taken from the kernel's own forward
     keep = None
     if p > 0:
-        _, z0, _ = F._ln_fwd(x, None, gam, bet, p, 1e-5, 77, True)       # z0 = dropout(x)
+        _, z0, _, _ = F._ln_fwd(x, None, gam, bet, p, 1e-5, 77, True)    # z0 = dropout(x)
         keep = (z0 != 0) | (x == 0)
     xr = x.float().requires_grad_(True)
     rr = res.float().requires_grad_(True)

@@ -34,14 +34,17 @@ def timeit(fn, n=10):
 
 
 for p in (0.0, 0.1):
-    y, z, st = F._ln_fwd(x, res, gam, bet, p, 1e-5, 1234, True)
+    y, z, st, bits = F._ln_fwd(x, res, gam, bet, p, 1e-5, 1234, True)
     t = timeit(lambda: F._ln_fwd(x, res, gam, bet, p, 1e-5, 1234, True))
     print(f'dropout_add_ln_fwd p={p}: {t:.1f} us  ({4 * R * C * 2 / t / 1e3:.0f} GB/s incl. allocation of outputs)')
     outs = {}
     for tma in (1, 0):
         lib.ver_debug_ln_bwd_tma(tma)
-        outs[tma] = F._ln_bwd(dy, z, st, gam, p, 1234)
-        t = timeit(lambda: F._ln_bwd(dy, z, st, gam, p, 1234))
+        outs[tma] = F._ln_bwd(dy, z, st, gam, p, 1234, bits)
+        t = timeit(lambda: F._ln_bwd(dy, z, st, gam, p, 1234, bits))
+        if bits is not None:
+            t2 = timeit(lambda: F._ln_bwd(dy, z, st, gam, p, 1234, None))
+            print(f'  (mask regenerated instead of read: {t2:.1f} us)')
         print(f'dropout_add_ln_bwd p={p} {"TMA ring" if tma else "register loads"}: {t:.1f} us  '
               f'({4 * R * C * 2 / t / 1e3:.0f} GB/s incl. partial sums + fold)')
     lib.ver_debug_ln_bwd_tma(1)

@@ -62,6 +62,10 @@ def _load():
         'ver_dropout_add_layernorm_fwd': (c_int, [c_int, P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float,
                                                   ctypes.c_uint64, P, P]),
         'ver_dropout_add_layernorm_bwd_blocks': (c_int, [c_int64]),
+        'ver_dropout_add_layernorm_fwd_bits': (c_int, [c_int, P, P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float,
+                                                       ctypes.c_uint64, P, P]),
+        'ver_dropout_add_layernorm_bwd_bits': (c_int, [c_int, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_float,
+                                                       ctypes.c_uint64, P, P]),
         'ver_dropout_add_layernorm_bwd': (c_int, [c_int, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_float,
                                                   ctypes.c_uint64, P, P]),
         'ver_relu_dropout_fwd': (c_int, [c_int, P, P, c_int64, c_float, ctypes.c_uint64, P, P]),

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256)
 dropout_add_ln_fwd(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                    const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ z_out,
                    float2* __restrict__ stats, int64_t rows, int C, float eps, float p, uint64_t seed,
-                   const unsigned long long* __restrict__ seed_epoch) {
+                   const unsigned long long* __restrict__ seed_epoch, uint8_t* __restrict__ keep_bits) {
     if (seed_epoch) seed += *seed_epoch;        // device-side word: fresh masks on every replay of a captured graph
     // gamma / beta staged in shared memory as [lo | hi][C / 8] float4: a lane's 8 columns are two conflict-free
     // 16-byte reads.  (Reading them from global cost 32 L1 sectors per warp request -- lane stride 32 B -- and made
@@ -90,6 +90,7 @@ dropout_add_ln_fwd(const T* __restrict__ x, const T* __restrict__ res, const flo
                 vx.get(v[k]);
                 if (p > 0.f) {
                     const uint32_t m = keep8((uint64_t)row * C + c, seed, thr16);
+                    if (keep_bits) keep_bits[((uint64_t)row * C + c) >> 3] = (uint8_t)m;     // one byte per 8 elements
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v[k][e] = ((m >> e) & 1) ? v[k][e] * scale : 0.f;
                 }
@@ -162,7 +163,8 @@ __global__ void __launch_bounds__(256, 2)
 dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const float2* __restrict__ stats,
                    const float* __restrict__ gamma, T* __restrict__ dx, T* __restrict__ dres,
                    float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, float* __restrict__ dxsum_part,
-                   int64_t rows, int C, float p, uint64_t seed, const unsigned long long* __restrict__ seed_epoch) {
+                   int64_t rows, int C, float p, uint64_t seed, const unsigned long long* __restrict__ seed_epoch,
+                   const uint8_t* __restrict__ keep_bits) {
     if (seed_epoch) seed += *seed_epoch;
     extern __shared__ float s_part[];       // [8 warps][C], reused for the three reductions
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -241,7 +243,8 @@ dropout_add_ln_bwd(const T* __restrict__ dy, const T* __restrict__ z, const floa
                     o.store(dres + row * C + c);
                 }
                 if (p > 0.f) {
-                    const uint32_t m = keep8((uint64_t)row * C + c, seed, thr16);
+                    const uint32_t m = keep_bits ? (uint32_t)keep_bits[((uint64_t)row * C + c) >> 3]
+                                                 : keep8((uint64_t)row * C + c, seed, thr16);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) dz[e] = ((m >> e) & 1) ? dz[e] * scale : 0.f;
                 }
@@ -292,7 +295,8 @@ __global__ void __launch_bounds__(256, 2)
 dropout_add_ln_bwd_tma(const __half* __restrict__ dy, const __half* __restrict__ z, const float2* __restrict__ stats,
                        const float* __restrict__ gamma, __half* __restrict__ dx, __half* __restrict__ dres,
                        float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, float* __restrict__ dxsum_part,
-                       int64_t rows, int C, float p, uint64_t seed, const unsigned long long* __restrict__ seed_epoch) {
+                       int64_t rows, int C, float p, uint64_t seed, const unsigned long long* __restrict__ seed_epoch,
+                       const uint8_t* __restrict__ keep_bits) {
     if (seed_epoch) seed += *seed_epoch;
     // [8 warps][kLnStages][dy row | z row]; the first 8 * C floats double as the reduction buffer at the end
     extern __shared__ __align__(128) unsigned char s_ring[];
@@ -337,6 +341,12 @@ dropout_add_ln_bwd_tma(const __half* __restrict__ dy, const __half* __restrict__
     for (int64_t row = row0; row < rows; row += stride, ++it) {
         const int st = (int)(it % kLnStages);
         const float2 stt = stats[row];
+        uint32_t mk[NV];                                // the forward's keep bits (in flight during the wait)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = (k * 32 + lane) * 8;
+            mk[k] = (keep_bits && p > 0.f && c < C) ? (uint32_t)keep_bits[((uint64_t)row * C + c) >> 3] : 0u;
+        }
         mbar_wait(&s_full[warp][st], (uint32_t)((it / kLnStages) & 1));
         const unsigned char* slot = my_ring + (size_t)st * 2 * row_bytes;
         float s1 = 0.f, s2 = 0.f;
@@ -389,7 +399,7 @@ dropout_add_ln_bwd_tma(const __half* __restrict__ dy, const __half* __restrict__
                     o.store(dres + row * C + c);
                 }
                 if (p > 0.f) {
-                    const uint32_t m = keep8((uint64_t)row * C + c, seed, thr16);
+                    const uint32_t m = keep_bits ? mk[k] : keep8((uint64_t)row * C + c, seed, thr16);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) dz[e] = ((m >> e) & 1) ? dz[e] * scale : 0.f;
                 }
@@ -553,6 +563,15 @@ extern "C" int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const voi
                                              const float* gamma, const float* beta, void* y, void* z_out,
                                              float* stats, int64_t rows, int C, float eps, float p_drop,
                                              uint64_t seed, const uint64_t* seed_epoch, ver_stream_t stream) {
+    return ver_dropout_add_layernorm_fwd_bits(dtype, x, residual, gamma, beta, y, z_out, stats, nullptr, rows, C, eps,
+                                              p_drop, seed, seed_epoch, stream);
+}
+
+extern "C" int ver_dropout_add_layernorm_fwd_bits(int dtype, const void* x, const void* residual,
+                                                  const float* gamma, const float* beta, void* y, void* z_out,
+                                                  float* stats, uint8_t* keep_bits, int64_t rows, int C, float eps,
+                                                  float p_drop, uint64_t seed, const uint64_t* seed_epoch,
+                                                  ver_stream_t stream) {
     const unsigned long long* ep = (const unsigned long long*)seed_epoch;
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
     VER_CHECK_ARG(x && gamma && beta && y, "null pointer");
@@ -562,9 +581,9 @@ extern "C" int ver_dropout_add_layernorm_fwd(int dtype, const void* x, const voi
     const int nv = (C + 255) / 256;
     const int grid = ln_grid(rows);
     if (dtype == VER_F16)
-        LN_DISPATCH(dropout_add_ln_fwd, __half, nv, <<<grid, 256, 0, st>>>((const __half*)x, (const __half*)residual, gamma, beta, (__half*)y, (__half*)z_out, (float2*)stats, rows, C, eps, p_drop, seed, ep));
+        LN_DISPATCH(dropout_add_ln_fwd, __half, nv, <<<grid, 256, 0, st>>>((const __half*)x, (const __half*)residual, gamma, beta, (__half*)y, (__half*)z_out, (float2*)stats, rows, C, eps, p_drop, seed, ep, keep_bits));
     else
-        LN_DISPATCH(dropout_add_ln_fwd, float, nv, <<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y, (float*)z_out, (float2*)stats, rows, C, eps, p_drop, seed, ep));
+        LN_DISPATCH(dropout_add_ln_fwd, float, nv, <<<grid, 256, 0, st>>>((const float*)x, (const float*)residual, gamma, beta, (float*)y, (float*)z_out, (float2*)stats, rows, C, eps, p_drop, seed, ep, keep_bits));
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;
     return VER_OK;
@@ -584,6 +603,15 @@ extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const vo
                                              float* dgamma_part, float* dbeta_part, float* dxsum_part,
                                              int64_t rows, int C, float p_drop, uint64_t seed,
                                              const uint64_t* seed_epoch, ver_stream_t stream) {
+    return ver_dropout_add_layernorm_bwd_bits(dtype, dy, z, stats, gamma, nullptr, dx, dresidual, dgamma_part, dbeta_part,
+                                              dxsum_part, rows, C, p_drop, seed, seed_epoch, stream);
+}
+
+extern "C" int ver_dropout_add_layernorm_bwd_bits(int dtype, const void* dy, const void* z, const float* stats,
+                                                  const float* gamma, const uint8_t* keep_bits, void* dx,
+                                                  void* dresidual, float* dgamma_part, float* dbeta_part,
+                                                  float* dxsum_part, int64_t rows, int C, float p_drop, uint64_t seed,
+                                                  const uint64_t* seed_epoch, ver_stream_t stream) {
     const unsigned long long* ep = (const unsigned long long*)seed_epoch;
     VER_CHECK_ARG(dtype == VER_F32 || dtype == VER_F16, "bad dtype %d", dtype);
     VER_CHECK_ARG(dy && z && stats && gamma && dx && dgamma_part && dbeta_part, "null pointer");
@@ -599,7 +627,7 @@ extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const vo
         cudaFuncSetAttribute(dropout_add_ln_bwd_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
         cudaFuncSetAttribute(dropout_add_ln_bwd_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
         cudaFuncSetAttribute(dropout_add_ln_bwd_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
-#define LN_TMA(NVV) dropout_add_ln_bwd_tma<NVV><<<grid, 256, ring, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep)
+#define LN_TMA(NVV) dropout_add_ln_bwd_tma<NVV><<<grid, 256, ring, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep, keep_bits)
         if (nv <= 1) LN_TMA(1);
         else if (nv <= 2) LN_TMA(2);
         else if (nv <= 3) LN_TMA(3);
@@ -610,13 +638,13 @@ extern "C" int ver_dropout_add_layernorm_bwd(int dtype, const void* dy, const vo
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(dropout_add_ln_bwd<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        LN_DISPATCH(dropout_add_ln_bwd, __half, nv, <<<grid, 256, smem, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep));
+        LN_DISPATCH(dropout_add_ln_bwd, __half, nv, <<<grid, 256, smem, st>>>((const __half*)dy, (const __half*)z, (const float2*)stats, gamma, (__half*)dx, (__half*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep, keep_bits));
     } else {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(dropout_add_ln_bwd<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(dropout_add_ln_bwd<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        LN_DISPATCH(dropout_add_ln_bwd, float, nv, <<<grid, 256, smem, st>>>((const float*)dy, (const float*)z, (const float2*)stats, gamma, (float*)dx, (float*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep));
+        LN_DISPATCH(dropout_add_ln_bwd, float, nv, <<<grid, 256, smem, st>>>((const float*)dy, (const float*)z, (const float2*)stats, gamma, (float*)dx, (float*)dresidual, dgamma_part, dbeta_part, dxsum_part, rows, C, p_drop, seed, ep, keep_bits));
     }
     VER_CHECK_LAUNCH();
     g_ver_launches += 1;

@@ -89,25 +89,29 @@ def f32_cat(*params):
 
 # ------------------------------------------------------------------ thin kernel wrappers (no autograd)
 def _ln_fwd(x, res, gamma32, beta32, p, eps, seed, save):
+    """-> y, z (the LayerNorm input), stats (mean, rstd per row), keep bits of the dropout mask (one byte per 8
+    elements; None without dropout): the last three are what backward needs."""
     rows, C = x.shape
     y = torch.empty_like(x)
     z = torch.empty_like(x) if save else None
     stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if save else None
-    check(lib.ver_dropout_add_layernorm_fwd(VER_F16, _ptr(x), _ptr(res), _ptr(gamma32), _ptr(beta32), _ptr(y),
-                                            _ptr(z), _ptr(stats), rows, C, float(eps), float(p), seed,
-                                            _ptr(ops._seed_epoch(x.device)), _stream()))
-    return y, z, stats
+    bits = torch.empty(rows * C // 8, dtype=torch.uint8, device=x.device) if (save and p > 0) else None
+    check(lib.ver_dropout_add_layernorm_fwd_bits(VER_F16, _ptr(x), _ptr(res), _ptr(gamma32), _ptr(beta32), _ptr(y),
+                                                 _ptr(z), _ptr(stats), _ptr(bits), rows, C, float(eps), float(p), seed,
+                                                 _ptr(ops._seed_epoch(x.device)), _stream()))
+    return y, z, stats, bits
 
 
-def _ln_bwd(dy, z, stats, gamma32, p, seed):
-    """-> dx (gradient of the dropout input), dres (gradient of the residual input), dgamma, dbeta, colsum(dx)."""
+def _ln_bwd(dy, z, stats, gamma32, p, seed, bits=None):
+    """-> dx (gradient of the dropout input), dres (gradient of the residual input), dgamma, dbeta, colsum(dx).
+    `bits`: the forward's keep bits; None regenerates the mask from (seed, element index)."""
     rows, C = z.shape
     dx, dres = torch.empty_like(z), torch.empty_like(z)
     nb = lib.ver_dropout_add_layernorm_bwd_blocks(rows)
     part = torch.empty((3, nb, C), dtype=torch.float32, device=z.device)
-    check(lib.ver_dropout_add_layernorm_bwd(VER_F16, _ptr(dy), _ptr(z), _ptr(stats), _ptr(gamma32), _ptr(dx),
-                                            _ptr(dres), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), rows, C,
-                                            float(p), seed, _ptr(ops._seed_epoch(z.device)), _stream()))
+    check(lib.ver_dropout_add_layernorm_bwd_bits(VER_F16, _ptr(dy), _ptr(z), _ptr(stats), _ptr(gamma32), _ptr(bits),
+                                                 _ptr(dx), _ptr(dres), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]),
+                                                 rows, C, float(p), seed, _ptr(ops._seed_epoch(z.device)), _stream()))
     folded = _fold_mats(part)                       # dgamma, dbeta, colsum(dx) in one launch
     return dx, dres, folded[0], folded[1], folded[2]
 
@@ -272,7 +276,7 @@ class VoxelLayerFunction(Function):
             proj = torch.addmm(half_of(bo), slots, Wo16.t())
         seed1, seed2, seed3 = ops._next_seed(), ops._next_seed(), ops._next_seed()
         g1f, be1f, g2f, be2f = (t.detach().float().contiguous() for t in (g1, be1, g2, be2))
-        y1, z1, st1 = _ln_fwd(proj, q, g1f, be1f, p_attn, eps1, seed1, need_bwd)
+        y1, z1, st1, kb1 = _ln_fwd(proj, q, g1f, be1f, p_attn, eps1, seed1, need_bwd)
         del proj
         ops.nvtx_pop()
         # FFN: Linear -> ReLU -> Dropout -> Linear -> Dropout, + identity, LayerNorm
@@ -288,12 +292,13 @@ class VoxelLayerFunction(Function):
             f = ops.linear_tc(h, W216, b2, ops.LINEAR_BIAS_F16)
         else:
             f = torch.addmm(half_of(b2), h, W216.t())
-        y2, z2, st2 = _ln_fwd(f, y1, g2f, be2f, p_out, eps2, seed3, need_bwd)
+        y2, z2, st2, kb2 = _ln_fwd(f, y1, g2f, be2f, p_out, eps2, seed3, need_bwd)
         del f
         ops.nvtx_pop()
         if need_bwd:
             ctx.save_for_backward(q, feat, vimg, logits, slots, z1, st1, y1, h, z2, st2, Wv16, Wcat16, Wo16, W116,
-                                  W216, g1f, g2f)
+                                  W216, g1f, g2f, *(t for t in (kb1, kb2) if t is not None))
+            ctx.has_bits = (kb1 is not None, kb2 is not None)
             ctx.vis, ctx.dims = vis, (B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP)
             ctx.drop = (p_attn, seed1, p_ffn, p_out, seed3)
             ctx.n_so = Wso.shape[0]
@@ -305,7 +310,10 @@ class VoxelLayerFunction(Function):
     @once_differentiable
     def backward(ctx, dy2):
         (q, feat, vimg, logits, slots, z1, st1, y1, h, z2, st2, Wv16, Wcat16, Wo16, W116, W216, g1f,
-         g2f) = ctx.saved_tensors
+         g2f) = ctx.saved_tensors[:18]
+        extra = list(ctx.saved_tensors[18:])
+        kb1 = extra.pop(0) if ctx.has_bits[0] else None           # dropout keep bits of the two LayerNorm inputs
+        kb2 = extra.pop(0) if ctx.has_bits[1] else None
         vis = ctx.vis
         B, Ncam, Z, H, W, Sh, Sw, NH, Dh, NP = ctx.dims
         p_attn, seed1, p_ffn, p_out, seed3 = ctx.drop
@@ -315,7 +323,7 @@ class VoxelLayerFunction(Function):
             dy2 = dy2.to(torch.float16)
         # ---- norm 2 / FFN
         ops.nvtx_push('layer.bwd.ffn+norm')
-        df, dy1, dg2, dbe2, db2 = _ln_bwd(dy2, z2, st2, g2f, p_out, seed3)
+        df, dy1, dg2, dbe2, db2 = _ln_bwd(dy2, z2, st2, g2f, p_out, seed3, kb2)
         dW2 = torch.mm(df.t(), h, out_dtype=f32)
         if (TC_GEMM['ffn2_bwd'] and ctx.W2 is not None and h.shape[1] % 256 == 0 and df.shape[1] % 64 == 0):
             # dX of FFN2, ReLU / dropout backward and the column sums (= FFN1 bias gradient) in one tcgen05 GEMM
@@ -331,7 +339,7 @@ class VoxelLayerFunction(Function):
         ops.nvtx_pop()
         # ---- norm 1 / output_proj
         ops.nvtx_push('layer.bwd.output_proj+norm')
-        dproj, dq, dg1, dbe1, dbo = _ln_bwd(dy1, z1, st1, g1f, p_attn, seed1)
+        dproj, dq, dg1, dbe1, dbo = _ln_bwd(dy1, z1, st1, g1f, p_attn, seed1, kb1)
         del dy1
         dWo = torch.mm(dproj.t(), slots, out_dtype=f32)
         dslots = torch.mm(dproj, Wo16)
