@@ -155,7 +155,7 @@ def main():
             for i in (16, 18, 17, 19, 20, 21, 23, 22):
                 print(f'  [{i:2d}] {names_b2[i]:42s} {outb[i] / bc:10.0f}')
     _lib.lib.ver_debug_bwd_variant(0)
-    if '--no-legacy' in sys.argv:
+    if '--no-legacy' in sys.argv or '--bwd-only' in sys.argv:
         return
     ops.TC_FORWARD = 'block'
     fn = _lib.lib.ver_debug_tc_timing
