@@ -213,16 +213,28 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         d.bits = ldg_pin(vis_bits + (size_t)b * Nq + n);
     };
     constexpr int kG = (kB2Hits * CG + kB2Threads - 1) / kB2Threads;
+    // 16-byte piece i of the G image -> (hit row, channel group): a warp instruction covers 8 rows x 4 channel groups,
+    // lane = (channel group, row % 8).  The 8 lanes of a store phase then write the 8 rows of ONE core matrix (128
+    // contiguous bytes, conflict free) and 4 lanes read 64 contiguous bytes of a row.  (Row-contiguous lanes -- 12 per
+    // row -- stored at a 128-byte stride: 8-way bank conflicts, 1 344 of ~2 900 shared-memory wavefronts per chunk,
+    // profiles/r02t_sca_bwd_tc2.txt.)
+    static_assert(CG % 4 == 0, "channel groups come in fours");
+    auto piece = [&](int i, int& rr, int& cg) {
+        const int wi = i >> 5, l = i & 31;
+        rr = (wi / (CG / 4)) * 8 + (l & 7);
+        cg = (wi % (CG / 4)) * 4 + (l >> 3);
+    };
     auto load_g = [&](const int* sn, uint4 (&gv)[kG]) {
 #pragma unroll
         for (int u = 0; u < kG; ++u) {
             const int i = tid + u * kB2Threads;
             gv[u] = make_uint4(0, 0, 0, 0);
             if (i < kB2Hits * CG) {
-                const int n = sn[i / CG];
+                int rr, cg;
+                piece(i, rr, cg);
+                const int n = sn[rr];
                 if (n >= 0)
-                    gv[u] = ldg_pin(reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH +
-                                                                   (i % CG) * 8));
+                    gv[u] = ldg_pin(reinterpret_cast<const uint4*>(gslots + ((size_t)b * Nq + n) * NH * DH + h * DH + cg * 8));
             }
         }
     };
@@ -273,7 +285,8 @@ sca_bwd_tc2_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         for (int u = 0; u < kG; ++u) {
             const int i = tid + u * kB2Threads;
             if (i < kB2Hits * CG) {
-                const int rr = i / CG, cg = i % CG;
+                int rr, cg;
+                piece(i, rr, cg);
                 *reinterpret_cast<uint4*>(Gimg + ((rr >> 3) * CG + cg) * 64 + (rr & 7) * 8) = g_cur[u];
             }
         }
