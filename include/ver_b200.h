@@ -191,14 +191,15 @@ int ver_sca_forward_sorted(const void* vimg, const float* logits, int ld_logits,
  * rows are built by two threads per row straight into the shared-memory tensor-core operand.
  *   ver_value_image16_f16: value [Bv, Sh*Sw, NH*Dh] fp16 -> vimg16 [Bv, NH, Dh/8, 2*Sh, 8, 8] fp16, cell k = y*16 + x + 1
  *   of pixel (y, x), the other cells of an image row zero.  Requires Sw <= 14.
- *   ver_sca_forward_sorted16: arguments as ver_sca_forward_sorted with vimg16 in place of vimg.  Requires
+ *   ver_sca_forward_sorted16: arguments as ver_sca_forward_sorted with vimg16 in place of vimg; variant 0 = default,
+ *   7 = sca_fwd_tc7_kernel (rows in a lane-interleaved scratch, A operand in TMEM), 6 = sca_fwd_tc6_kernel.  Requires
  *   ver_tc6_supported(): Ncam <= 32, 2 <= Sh, Sw <= 14, Dh in {32, 64, 96}, NP in {4, 8}. */
 int ver_tc6_supported(int Ncam, int Sh, int Sw, int Dh, int NP);
 int ver_value_image16_f16(const void* value, void* vimg16, int Bv, int Sh, int Sw, int NH, int Dh, ver_stream_t stream);
 int ver_sca_forward_sorted16(const void* vimg16, const float* logits, int ld_logits, const float* rpc,
                              const int32_t* order, const uint32_t* smask, const uint32_t* tile_union,
                              void* slots, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
-                             ver_stream_t stream);
+                             int variant, ver_stream_t stream);
 
 /* Backward of ver_sca_forward.
  *   grad_slots  [B, Nq, NH*Dh] dtype

@@ -667,7 +667,7 @@ def _offset_grad_comparable(rpc, mask, logits, B, ncam, Nq, NH, NP=8, S=14, eps=
     return full
 
 
-@pytest.mark.parametrize('fwd', ['sorted', 'sorted16', 'sorted5', 'sorted3', 'block'])
+@pytest.mark.parametrize('fwd', ['sorted', 'sorted16', 'sorted16_6', 'sorted5', 'sorted3', 'block'])
 @pytest.mark.parametrize('Dh,grid,B', [(96, (8, 20, 20), 2), (32, (3, 5, 7), 2), (64, (4, 8, 8), 1), (96, (3, 11, 13), 3)])
 def test_tc_sampler_forward_backward_vs_oracle(Dh, grid, B, fwd, monkeypatch):
     _check_tc_sampler(Dh, grid, B, fwd, monkeypatch)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over the tensor-core sampler kernels (SURVEY section 5 aux row).
-# Smallest parity case of every kernel generation: forward tc3 / tc4 / tc5 / block, backward tc2 / tc.
+# Smallest parity case of every kernel generation: forward tc3 / tc4 / tc5 / tc6 / tc7 / block, backward tc2 / tc.
 #   bash tools/sanitize.sh   (on the GPU box; writes gpurun_out/sanitizer/*.txt)
 set -u
 mkdir -p gpurun_out/sanitizer

@@ -12,25 +12,30 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vln_ver_b200 import _lib, ops, synth  # noqa: E402
 
 L = _lib.lib
-L.ver_debug_tc6.restype = ctypes.c_int
-L.ver_debug_tc6.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_uint)]
+for _n in ('ver_debug_tc6', 'ver_debug_tc7'):
+    getattr(L, _n).restype = ctypes.c_int
+    getattr(L, _n).argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_uint)]
 CODES = {1: 'control: built', 2: 'control: V landed', 3: 'control: accumulator drained', 4: 'control: V buffer free',
          5: 'control: drain', 6: 'epilogue: accumulator full', 7: 'builder: batch retired'}
-PHASES = {0: 'B: setup', 1: 'B: item top', 2: 'B: wait MMA retire', 3: 'B: un-tap', 4: 'B: taps', 6: 'B: fences + arrive',
+PHASES = {0: 'B: setup', 1: 'B: item top', 2: 'B: wait MMA retire', 3: 'B: un-tap (tc6) / copy + un-tap (tc7)', 4: 'B: taps', 6: 'B: fences + arrive',
           7: 'B: item end', 9: 'C: wait built', 10: 'C: wait V', 11: 'C: MMA issue', 12: 'C: V buffer wait + TMA',
           13: 'C: wait drained accumulator', 16: 'E: wait full accumulator', 17: 'E: TMEM->slots'}
 
 
-def debug(flags, tag=None):
-    """set the flags; returns (aborted, timers) of what ran since the last call"""
+def debug(flags, tag=None, which=('ver_debug_tc6', 'ver_debug_tc7')):
+    """set the flags of both kernels; returns (aborted, timers of the LAST kernel in `which`) of what ran since the last call"""
     torch.cuda.synchronize()
-    t = (ctypes.c_ulonglong * 32)()
-    d = (ctypes.c_uint * 8)()
-    aborted = L.ver_debug_tc6(flags, t, d)
-    if aborted and tag:
-        print(f'{tag}: WAIT TIMED OUT: {CODES.get(d[0], d[0])}, block {d[1]}, thread {d[2]}, words {d[3]} {d[4]}',
-              flush=True)
-    return aborted, list(t)
+    aborted, timers = 0, None
+    for name in which:
+        t = (ctypes.c_ulonglong * 32)()
+        d = (ctypes.c_uint * 8)()
+        a = getattr(L, name)(flags, t, d)
+        if a and tag:
+            print(f'{tag} [{name}]: WAIT TIMED OUT: {CODES.get(d[0], d[0])}, block {d[1]}, thread {d[2]}, words {d[3]} {d[4]}',
+                  flush=True)
+        aborted |= a
+        timers = list(t)
+    return aborted, timers
 
 
 def case(B, grid, Dh, time_it, sh=14, sw=14, seed=1235):
@@ -56,12 +61,15 @@ def case(B, grid, Dh, time_it, sh=14, sw=14, seed=1235):
                                             smask.data_ptr(), tu.data_ptr(), slots.data_ptr(), B, ncam, Nq, sh, sw, NH,
                                             Dh, 8, 4, st))
 
-    def run6(slots):
-        _lib.check(L.ver_sca_forward_sorted16(vimg16.data_ptr(), logits.data_ptr(), 192, rpc.data_ptr(),
-                                              order.data_ptr(), smask.data_ptr(), tu.data_ptr(), slots.data_ptr(), B,
-                                              ncam, Nq, sh, sw, NH, Dh, 8, st))
+    def run16(variant):
+        def run(slots):
+            _lib.check(L.ver_sca_forward_sorted16(vimg16.data_ptr(), logits.data_ptr(), 192, rpc.data_ptr(),
+                                                  order.data_ptr(), smask.data_ptr(), tu.data_ptr(), slots.data_ptr(), B,
+                                                  ncam, Nq, sh, sw, NH, Dh, 8, variant, st))
+        return run
+    run6, run7 = run16(6), run16(7)
     outs = {}
-    for name, run in (('tc4', run4), ('tc6', run6)):
+    for name, run in (('tc4', run4), ('tc7', run7), ('tc6', run6)):
         slots = torch.full((B, Nq, NH * Dh), float('nan'), dtype=torch.float16, device='cuda')
         run(slots)
         if debug(2, f'B={B} grid={grid} Dh={Dh} {name}')[0]:
@@ -81,25 +89,30 @@ def case(B, grid, Dh, time_it, sh=14, sw=14, seed=1235):
             print(f'  {name}: median {ts[4] * 1e3:.1f} us, min {ts[0] * 1e3:.1f} us', flush=True)
             if debug(2, 'timing loop')[0]:
                 return False
-    a, b = outs['tc4'].float(), outs['tc6'].float()
-    nan = int(torch.isnan(b).sum().item())
-    d = ((a - b).abs().max() / a.abs().max()).item()
-    print(f'B={B} grid={grid} Dh={Dh} map {sh}x{sw}: max |tc6 - tc4| / max |tc4| = {d:.2e}, NaNs in tc6 output: {nan}',
-          flush=True)
+    a = outs['tc4'].float()
+    ok = True
+    for name in ('tc7', 'tc6'):
+        b = outs[name].float()
+        nan = int(torch.isnan(b).sum().item())
+        d = ((a - b).abs().max() / a.abs().max()).item()
+        print(f'B={B} grid={grid} Dh={Dh} map {sh}x{sw}: max |{name} - tc4| / max |tc4| = {d:.2e}, NaNs: {nan}', flush=True)
+        ok &= nan == 0 and d < 2e-3
+    print(f'  tc7 == tc6 bit for bit: {torch.equal(outs["tc7"], outs["tc6"])}')
     if time_it:
-        debug(3)
-        slots = torch.empty((B, Nq, NH * Dh), dtype=torch.float16, device='cuda')
-        flush.zero_()
-        run6(slots)
-        _, t = debug(2)
-        print('  phase timers (SM cycles summed over 148 CTAs / 148):')
-        for k, name in PHASES.items():
-            print(f'    [{k:2d}] {name:32s} {t[k] / 148:10.0f}')
-    return nan == 0 and d < 2e-3
+        for name, run, hook in (('tc7', run7, 'ver_debug_tc7'), ('tc6', run6, 'ver_debug_tc6')):
+            debug(3)
+            slots = torch.empty((B, Nq, NH * Dh), dtype=torch.float16, device='cuda')
+            flush.zero_()
+            run(slots)
+            _, t = debug(2, which=(hook,))
+            print(f'  {name} phase timers (SM cycles summed over 148 CTAs / 148):')
+            for k, pname in PHASES.items():
+                print(f'    [{k:2d}] {pname:40s} {t[k] / 148:10.0f}')
+    return ok
 
 
 def main():
-    assert L.ver_debug_tc6(2, None, None) == 0          # watchdog: report, do not trap
+    assert L.ver_debug_tc6(2, None, None) == 0 and L.ver_debug_tc7(2, None, None) == 0      # watchdog: report, do not trap
     ok = True
     ok &= case(1, (3, 5, 7), 32, False)
     ok &= case(2, (8, 20, 20), 96, False)

@@ -25,7 +25,14 @@ def main():
     order, smask, tu = vis.order
     vimg = ops.value_image(value, NH)
     slots = torch.empty((B, Nq, NH * Dh), dtype=torch.float16, device='cuda')
+    vimg16 = ops.value_image16(value, NH, 14, 14) if variant in (6, 7) else None
     for _ in range(3):
+        if variant in (6, 7):          # generations on 16-cell image rows
+            _lib.check(_lib.lib.ver_sca_forward_sorted16(vimg16.data_ptr(), logits.data_ptr(), 192, rpc.data_ptr(),
+                                                         order.data_ptr(), smask.data_ptr(), tu.data_ptr(),
+                                                         slots.data_ptr(), B, ncam, Nq, 14, 14, NH, Dh, 8, variant,
+                                                         torch.cuda.current_stream().cuda_stream))
+            continue
         _lib.check(_lib.lib.ver_sca_forward_sorted(vimg.data_ptr(), logits.data_ptr(), 192, rpc.data_ptr(),
                                                    order.data_ptr(), smask.data_ptr(), tu.data_ptr(),
                                                    slots.data_ptr(), B, ncam, Nq, 14, 14, NH, Dh, 8, variant,

@@ -56,7 +56,7 @@ def _load():
         'ver_value_image_f16': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
         'ver_value_image16_f16': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
         'ver_tc6_supported': (c_int, [c_int] * 5),
-        'ver_sca_forward_sorted16': (c_int, [P, P, c_int, P, P, P, P, P] + [c_int] * 8 + [P]),
+        'ver_sca_forward_sorted16': (c_int, [P, P, c_int, P, P, P, P, P] + [c_int] * 9 + [P]),
         'ver_feat_embed': (c_int, [c_int, P, P, P, P, c_int, c_int, c_int, c_int, P]),
         'ver_add_layernorm': (c_int, [c_int, P, P, P, P, P, c_int64, c_int, c_float, P]),
         'ver_dropout_add_layernorm_fwd': (c_int, [c_int, P, P, P, P, P, P, P, c_int64, c_int, c_float, c_float,

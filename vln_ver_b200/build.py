@@ -11,7 +11,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 LIB = os.path.join(HERE, 'libver_b200.so')
 STAMP = os.path.join(HERE, '.libver_b200.stamp')
 
-SOURCES = ['api.cu', 'geometry.cu', 'msda.cu', 'msda3d.cu', 'col2im.cu', 'sca.cu', 'sca_tc.cu', 'sca_tc3.cu', 'sca_tc4.cu', 'sca_tc5.cu', 'sca_tc6.cu', 'sca_bwd_tc2.cu', 'order.cu', 'gemm_tc.cu', 'elementwise.cu',
+SOURCES = ['api.cu', 'geometry.cu', 'msda.cu', 'msda3d.cu', 'col2im.cu', 'sca.cu', 'sca_tc.cu', 'sca_tc3.cu', 'sca_tc4.cu', 'sca_tc5.cu', 'sca_tc6.cu', 'sca_tc7.cu', 'sca_bwd_tc2.cu', 'order.cu', 'gemm_tc.cu', 'elementwise.cu',
            'fused_norm.cu']
 NVCC_FLAGS = ['--threads', '8', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--shared']

@@ -53,6 +53,11 @@ int ver_tc4_supported(int Ncam, int S, int Dh, int NP);
 int ver_sca_forward_tc4(const void* vimg, const float* logits, int ld, const float* rpc, const int32_t* order,
                         const uint32_t* smask, const uint32_t* tile_union, void* slots, int B, int Ncam, int Nq,
                         int Sh, int Sw, int NH, int Dh, int NP, cudaStream_t st);
+// two-threads-per-row builder in front of the TMEM A operand, 16-cell image rows, sca_tc7.cu
+int ver_tc7_supported(int Ncam, int Sh, int Sw, int Dh, int NP);
+int ver_sca_forward_tc7(const void* vimg16, const float* logits, int ld_logits, const float* rpc, const int32_t* order,
+                        const uint32_t* smask, const uint32_t* tile_union, void* slots, int B, int Ncam, int Nq, int Sh,
+                        int Sw, int NH, int Dh, int NP, cudaStream_t st);
 // three-operand software-pipelined sorted-row forward, sca_tc5.cu
 int ver_tc5_supported(int Ncam, int S, int Dh, int NP);
 int ver_sca_forward_tc5(const void* vimg, const float* logits, int ld, const float* rpc, const int32_t* order,

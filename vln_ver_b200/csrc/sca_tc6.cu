@@ -625,8 +625,9 @@ extern "C" int ver_value_image16_f16(const void* value, void* vimg, int Bv, int 
 extern "C" int ver_sca_forward_sorted16(const void* vimg16, const float* logits, int ld_logits, const float* rpc,
                                         const int32_t* order, const uint32_t* smask, const uint32_t* tile_union,
                                         void* slots, int B, int Ncam, int Nq, int Sh, int Sw, int NH, int Dh, int NP,
-                                        ver_stream_t stream) {
+                                        int variant, ver_stream_t stream) {
     VER_CHECK_ARG(vimg16 && logits && rpc && order && smask && tile_union && slots, "null pointer");
+    VER_CHECK_ARG(variant == 0 || variant == 6 || variant == 7, "variant must be 0 (default), 6 or 7");
     VER_CHECK_ARG(B > 0 && Ncam > 0 && Nq > 0 && Sh > 0 && Sw > 0 && NH > 0, "non-positive dimension");
     VER_CHECK_ARG(ld_logits >= NH * NP * 3 && ld_logits % 4 == 0 && NP % 4 == 0,
                   "logits rows must be 16-byte aligned per head (NP %% 4 == 0, ld %% 4 == 0)");
@@ -635,6 +636,10 @@ extern "C" int ver_sca_forward_sorted16(const void* vimg16, const float* logits,
         return VER_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // variant 0 / 7: the TMEM-operand form (sca_fwd_tc7_kernel) where it applies; 6: A in the shared-memory operand
+    if (variant != 6 && ver_tc7_supported(Ncam, Sh, Sw, Dh, NP))
+        return ver_sca_forward_tc7(vimg16, logits, ld_logits, rpc, order, smask, tile_union, slots, B, Ncam, Nq, Sh, Sw, NH,
+                                   Dh, NP, st);
 #define FWD6(D)                                                                                                      \
     (NP == 8 ? launch_fwd_tc6<D, 8>((const __half*)vimg16, logits, ld_logits, rpc, order, smask, tile_union,         \
                                     (__half*)slots, B, Ncam, Nq, Sh, Sw, NH, st)                                     \

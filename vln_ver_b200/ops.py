@@ -459,8 +459,9 @@ def value_image16(value, NH, Sh, Sw):
     return vimg
 
 
-def sca_forward_sorted16(vimg16, logits, vis, Sh, Sw, NH, NP):
-    """Forward sampler on 16-cell image rows (sca_fwd_tc6_kernel): slots (B, Nq, C) fp16."""
+def sca_forward_sorted16(vimg16, logits, vis, Sh, Sw, NH, NP, variant=0):
+    """Forward sampler on 16-cell image rows: slots (B, Nq, C) fp16.  variant 0 / 7 = sca_fwd_tc7_kernel (A operand in
+    TMEM), 6 = sca_fwd_tc6_kernel (A in the shared-memory operand)."""
     _need_cuda(vimg16, logits)
     Ncam, B = vis.rpc.shape[:2]
     Z, H, W = vis.grid
@@ -472,7 +473,7 @@ def sca_forward_sorted16(vimg16, logits, vis, Sh, Sw, NH, NP):
     slots = torch.empty((B, Nq, NH * Dh), dtype=torch.float16, device=logits.device)
     check(lib.ver_sca_forward_sorted16(_ptr(vimg16), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
                                        _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw, NH, Dh, NP,
-                                       _stream()))
+                                       int(variant), _stream()))
     return slots
 
 
@@ -480,10 +481,12 @@ VER_LAYOUT_TC_IMAGE = 2
 # 'sorted': visibility-sorted rows, the fastest measured kernel generation that covers the shape
 # (sca_fwd_tc4_kernel); 'sorted3' / 'sorted4' / 'sorted5': force a generation (tests and tools/ A-B timing only;
 # sorted5 = sca_fwd_tc5_kernel: three A operands in TMEM, two issuing threads, bounded waits);
-# 'sorted16': sca_fwd_tc6_kernel on 16-cell image rows (two builder threads per row, A in the shared-memory operand;
-# measured slower than sorted4, kept as an experiment with its parity test); 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
+# 'sorted16' / 'sorted16_6': the generations on 16-cell image rows with two builder threads per row -- sca_fwd_tc7_kernel (A
+# operand in TMEM: 389 us against 408 us for sorted4, but it needs its own value image, ver_value_image16_f16, which the backward
+# cannot share) / sca_fwd_tc6_kernel (A in the shared-memory operand, 564 us); 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
 TC_FORWARD = 'sorted'
-_SORTED_VARIANT = {'sorted': 0, 'sorted3': 3, 'sorted4': 4, 'sorted5': 5, 'sorted16': 0}
+_SORTED_VARIANT = {'sorted': 0, 'sorted3': 3, 'sorted4': 4, 'sorted5': 5, 'sorted16': 0, 'sorted16_6': 0}
+_SORTED16_VARIANT = {'sorted16': 7, 'sorted16_6': 6}      # sca_fwd_tc7_kernel / sca_fwd_tc6_kernel
 
 
 class SCASampleTCFunction(Function):
@@ -509,8 +512,9 @@ class SCASampleTCFunction(Function):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if (TC_FORWARD == 'sorted16' and logits.shape[1] % 4 == 0 and lib.ver_tc6_supported(Ncam, Sh, Sw, Dh, NP)):
-            slots = sca_forward_sorted16(value_image16(value, NH, Sh, Sw), logits, vis, Sh, Sw, NH, NP)
+        if (TC_FORWARD in _SORTED16_VARIANT and logits.shape[1] % 4 == 0 and lib.ver_tc6_supported(Ncam, Sh, Sw, Dh, NP)):
+            slots = sca_forward_sorted16(value_image16(value, NH, Sh, Sw), logits, vis, Sh, Sw, NH, NP,
+                                         _SORTED16_VARIANT[TC_FORWARD])
         elif TC_FORWARD in _SORTED_VARIANT and NP % 4 == 0 and logits.shape[1] % 4 == 0:
             order, smask, tile_union = vis.order
             check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
