@@ -23,7 +23,8 @@
 // removes that wait but puts the epilogue on the critical path (465 us) -- kept as independent groups.
 //
 // Roles: warps 0-3 = group 0 (rows 0..127 of the chunk), warps 4-7 = group 1, warps 8-11 = epilogue (TMEM lane
-// quarter = warp % 4, both groups), warp 12 = control (one lane): TMA of the value images, MMA issue.
+// quarter = warp % 4, both groups), warps 12 / 13 = control (one lane each): MMA issue of group 0 / 1; warp 12 also issues
+// the TMA of the value images.
 // TMEM columns: [0, 2 DH) the two accumulators, [2 DH, 2 DH + SP) the two A operands (SP / 2 columns each).
 // Hand-offs (mbarriers):
 //     bar_built[g]    group g wrote A_g for its next camera into TMEM            (4 arrivals, one per warp)
@@ -37,7 +38,7 @@
 namespace {
 
 constexpr int kF4Workers = 256;
-constexpr int kF4Threads = kF4Workers + 128 + 32;
+constexpr int kF4Threads = kF4Workers + 128 + 64;        // 8 worker warps, 4 epilogue warps, 2 control warps
 constexpr int kF4Rows = 128;                  // rows per group = UMMA M
 constexpr int kF4ChunkRows = 2 * kF4Rows;
 // per-worker landing slot of the prefetches (cp.async): 24 fp32 logits of (row, head) | n, camera mask, tile
@@ -160,7 +161,7 @@ sca_fwd_tc4_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_free[i], 4);
             mbar_init(&bar_v[i], 1);
-            mbar_init(&bar_vfree[i], 1);
+            mbar_init(&bar_vfree[i], 2);
         }
         mbar_fence_init();
     }
@@ -174,12 +175,17 @@ sca_fwd_tc4_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
     const int nchunks = SP >> 4;
     const uint32_t tm_a0 = tmem + 2 * DH;                      // A operand of group g at + g * (SP / 2) columns
 
-    if (warp == 12) {
-        // ================================================================ control: TMA + MMA issue
+    if (warp >= 12) {
+        // ================================================================ control: one issuing thread per row group
+        // (warp 12: group 0 and the TMA of the value images, warp 13: group 1).  Both walk the same sequence of
+        // (item, camera) steps.  A single thread issuing both groups' batches one after the other delayed each group's
+        // MMAs by the other's issue time (round 2, profiles/r03c: the split took the sibling kernel sca_fwd_tc7_kernel
+        // from 409 to 389 us).
         if (lane == 0) {
+            const int cg = warp - 12;
             constexpr uint32_t idesc = umma_idesc(128, DH, 0, 0);
             int nx_item = (int)blockIdx.x - (int)gridDim.x;
-            uint32_t nx_rest = 0, nx_u0 = 0, nx_u1 = 0;
+            uint32_t nx_rest = 0, nx_ug = 0;
             int nx_b = 0, nx_h = 0, nx_cam = 0;
             auto advance = [&]() -> bool {
                 while (true) {
@@ -194,77 +200,83 @@ sca_fwd_tc4_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                     nx_b = it.b;
                     nx_h = it.h;
                     const uint32_t* tu = tile_union + (size_t)it.b * tiles_per_b + 2 * it.chunk;
-                    nx_u0 = tu[0];
-                    nx_u1 = (2 * it.chunk + 1 < tiles_per_b) ? tu[1] : 0u;
-                    nx_rest = nx_u0 | nx_u1;
+                    const uint32_t u0 = tu[0], u1 = (2 * it.chunk + 1 < tiles_per_b) ? tu[1] : 0u;
+                    nx_ug = cg ? u1 : u0;
+                    nx_rest = u0 | u1;
                 }
             };
             auto load_v = [&](int buf) {
                 mbar_expect_tx(&bar_v[buf], L.v_bytes);
-                bulk_g2s(smem + L.off_v[buf], vimg + ((size_t)(nx_b * Ncam + nx_cam) * NH + nx_h) * v_elems,
+                bulk_g2s(smem + (buf ? L.off_v[1] : L.off_v[0]), vimg + ((size_t)(nx_b * Ncam + nx_cam) * NH + nx_h) * v_elems,
                          L.v_bytes, &bar_v[buf]);
             };
-            F4Timer tc(true);
+            F4Timer tc(cg == 0);
             bool has_next = advance();
-            if (has_next) load_v(0);
-            uint32_t kk = 0, itg[2] = {0, 0}, acc_items[2] = {0, 0};
+            if (cg == 0 && has_next) load_v(0);
+            uint32_t kk = 0, itg = 0, acc_items = 0;
+            const uint64_t dv_0 = umma_desc(smem_u32(smem + L.off_v[0]), 128, G * 128);
+            const uint64_t dv_1 = umma_desc(smem_u32(smem + L.off_v[1]), 128, G * 128);
+            const uint32_t chunk_mask = (1u << nchunks) - 1u;
+            const uint32_t d_addr = tmem + cg * DH, a_addr = tm_a0 + cg * (SP >> 1);
             while (has_next) {
                 const int cam = nx_cam;
-                const uint32_t u[2] = {nx_u0, nx_u1};
+                const uint32_t ug = nx_ug;
                 has_next = advance();                  // nx_* now describe step kk + 1
                 const int buf = kk & 1;
-                bool first = true;
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    if (!((u[g] >> cam) & 1u)) continue;
-                    const bool first_cam = !(u[g] & ((1u << cam) - 1u));       // lowest camera of this tile overwrites
-                    const bool last_cam = !(u[g] >> (cam + 1));
-                    mbar_wait_park(&bar_built[g], itg[g] & 1);
+                // EVERY step, work or not: a parity wait is only valid for a waiter that observes every phase of the
+                // barrier -- a control thread whose group idles through some steps would otherwise run ahead of the
+                // value-image loads, pass a later wait early and desynchronise bar_vfree
+                mbar_wait_park(&bar_v[buf], (kk >> 1) & 1);
+                tc.lap(10);                            // control: wait for the value image
+                if ((ug >> cam) & 1u) {
+                    const bool first_cam = !(ug & ((1u << cam) - 1u));         // lowest camera of this tile overwrites
+                    const bool last_cam = !(ug >> (cam + 1));
+                    mbar_wait_park(&bar_built[cg], itg & 1);
                     tc.lap(9);                         // control: wait for a built A
-                    if (first) mbar_wait_park(&bar_v[buf], (kk >> 1) & 1);
-                    tc.lap(10);                        // control: wait for the value image
-                    if (first_cam && acc_items[g]) mbar_wait_park(&bar_free[g], (acc_items[g] - 1) & 1);
+                    if (first_cam && acc_items) mbar_wait_park(&bar_free[cg], (acc_items - 1) & 1);
                     tc_fence_after();
                     tc.lap(13);                        // control: wait for a drained accumulator
-                    const uint32_t v_addr = smem_u32(smem + L.off_v[buf]);
-                    const uint32_t a_addr = tm_a0 + g * (SP >> 1);
-                    const int par = itg[g] & 1;
-                    uint32_t km = s_kmask[g][par][0] | s_kmask[g][par][1] | s_kmask[g][par][2] | s_kmask[g][par][3];
-                    uint32_t acc = first_cam ? 0u : 1u;
-                    if (!acc && !km) km = 1u;          // (an all-zero chunk zeroes the accumulator)
-                    // straight-line issue: one descriptor per batch, compile-time increments per K chunk (a
-                    // find-first-set loop that rebuilds the descriptor costs ~150 cycles per MMA on the uniform datapath)
-                    const uint64_t dv0 = umma_desc(v_addr, 128, G * 128);
-                    const uint32_t d_addr = tmem + g * DH;
+                    const int par = itg & 1;
+                    uint32_t km = (s_kmask[cg][par][0] | s_kmask[cg][par][1] | s_kmask[cg][par][2] | s_kmask[cg][par][3]) & chunk_mask;
+                    if (first_cam && !km) km = 1u;     // (an all-zero chunk zeroes the accumulator)
+                    const uint64_t dvb = buf ? dv_1 : dv_0;
+                    // straight-line issue (a find-first-set loop that rebuilds the descriptor costs ~150 cycles per MMA on
+                    // the uniform datapath; an indexed descriptor array lives in local memory: one LDL per MMA), the
+                    // accumulate flag a compile-time constant except on an item's first camera
+                    if (first_cam) {
+                        const uint32_t first_bit = km & (0u - km);
 #pragma unroll
-                    for (int ks = 0; ks < 16; ++ks) {
-                        if ((km >> ks) & 1u) {
-                            umma_f16_ts(d_addr, a_addr + ks * 8, dv0 + (uint64_t)(ks * 16), idesc, acc);
-                            acc = 1u;
-                        }
+                        for (int ks = 0; ks < 16; ++ks)
+                            if ((km >> ks) & 1u)
+                                umma_f16_ts(d_addr, a_addr + ks * 8, dvb + (uint64_t)(ks * 16), idesc, (first_bit >> ks) & 1u ? 0u : 1u);
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 16; ++ks)
+                            if ((km >> ks) & 1u) umma_f16_ts(d_addr, a_addr + ks * 8, dvb + (uint64_t)(ks * 16), idesc, 1u);
                     }
-                    umma_commit(&bar_mma[g]);
+                    umma_commit(&bar_mma[cg]);
                     if (last_cam) {
-                        umma_commit(&bar_full[g]);
-                        ++acc_items[g];
+                        umma_commit(&bar_full[cg]);
+                        ++acc_items;
                     }
                     tc.lap(11);                        // control: MMA issue
-                    ++itg[g];
-                    if (first && has_next) {
-                        // value image of step kk + 1 -> the other buffer, once step kk - 1 stopped reading it
-                        if (kk >= 1) mbar_wait_park(&bar_vfree[(kk + 1) & 1], ((kk - 1) >> 1) & 1);
-                        load_v((kk + 1) & 1);
-                        tc.lap(12);                    // control: wait for a free value buffer + TMA issue
-                    }
-                    first = false;
+                    ++itg;
                 }
-                umma_commit(&bar_vfree[buf]);
+                // two arrivals per step, one from each control thread: behind my MMAs if I issued any, else a plain arrive
+                if ((ug >> cam) & 1u) umma_commit(&bar_vfree[buf]);
+                else mbar_arrive(&bar_vfree[buf]);
+                if (cg == 0 && has_next) {
+                    // value image of step kk + 1 -> the other buffer, once step kk - 1 stopped reading it
+                    if (kk >= 1) mbar_wait_park(&bar_vfree[(kk + 1) & 1], ((kk - 1) >> 1) & 1);
+                    load_v((kk + 1) & 1);
+                    tc.lap(12);                        // control: wait for a free value buffer + TMA issue
+                }
                 ++kk;
             }
             // drain: the last commits must have arrived before the CTA tears TMEM / smem down
             if (kk >= 1) mbar_wait_park(&bar_vfree[(kk - 1) & 1], ((kk - 1) >> 1) & 1);
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8) {         // (warps 8-11; the control warps were taken above)
         // ================================================================ epilogue: TMEM -> slots
         const int q = warp & 3, r = q * 32 + lane;              // TMEM lane quarter / row inside a group
         uint32_t full_seen[2] = {0, 0};
