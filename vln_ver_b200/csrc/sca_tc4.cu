@@ -32,6 +32,8 @@
 //     bar_full[g]     tcgen05.commit after the item's last camera: accumulator g is complete
 //     bar_free[g]     the epilogue warps drained accumulator g                  (4 arrivals)
 //     bar_v[buf] / bar_vfree[buf]   value image landed (transaction bytes) / all MMAs reading it retired
+#include <type_traits>
+
 #include "sampler.cuh"
 #include "tcgen05.cuh"
 
@@ -181,8 +183,10 @@ sca_fwd_tc4_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         // (item, camera) steps.  A single thread issuing both groups' batches one after the other delayed each group's
         // MMAs by the other's issue time (round 2, profiles/r03c: the split took the sibling kernel sca_fwd_tc7_kernel
         // from 409 to 389 us).
-        if (lane == 0) {
-            const int cg = warp - 12;
+        // (the group index is a compile-time constant inside: barrier and mask addresses are static, which is also what
+        // compute-sanitizer's barrier tracking wants)
+        auto control = [&](auto cg_const) {
+            constexpr int cg = decltype(cg_const)::value;
             constexpr uint32_t idesc = umma_idesc(128, DH, 0, 0);
             int nx_item = (int)blockIdx.x - (int)gridDim.x;
             uint32_t nx_rest = 0, nx_ug = 0;
@@ -275,6 +279,10 @@ sca_fwd_tc4_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             }
             // drain: the last commits must have arrived before the CTA tears TMEM / smem down
             if (kk >= 1) mbar_wait_park(&bar_vfree[(kk - 1) & 1], ((kk - 1) >> 1) & 1);
+        };
+        if (lane == 0) {
+            if (warp == 12) control(std::integral_constant<int, 0>{});
+            else control(std::integral_constant<int, 1>{});
         }
     } else if (warp >= 8) {         // (warps 8-11; the control warps were taken above)
         // ================================================================ epilogue: TMEM -> slots

@@ -22,6 +22,8 @@
 //     bar_free[g]     the epilogue warps drained accumulator g                  (4 arrivals)
 //     bar_v[buf] / bar_vfree[buf]   value image landed (transaction bytes) / all MMAs reading it retired (2 commits)
 //   named barrier 1 + w (64 threads): the two builder warps of rows 32 w .. share one prefetch slot (logits of the item)
+#include <type_traits>
+
 #include "sampler.cuh"
 #include "tcgen05.cuh"
 
@@ -194,8 +196,10 @@ sca_fwd_tc7_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
         // (warp 20: group 0 and the TMA of the value images, warp 21: group 1).  Both walk the same sequence of
         // (item, camera) steps; a single thread issuing both groups' batches one after the other delayed each group's
         // MMAs by the other's issue time.
-        if (lane == 0) {
-            const int cg = warp - 20;
+        // (the group index is a compile-time constant inside: barrier and mask addresses are static, which is also what
+        // compute-sanitizer's barrier tracking wants)
+        auto control = [&](auto cg_const) {
+            constexpr int cg = decltype(cg_const)::value;
             constexpr uint32_t idesc = umma_idesc(128, DH, 0, 0);
             int nx_item = (int)blockIdx.x - (int)gridDim.x;
             uint32_t nx_rest = 0, nx_ug = 0;
@@ -293,6 +297,10 @@ sca_fwd_tc7_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
             }
             // drain: the last commits must have arrived before the CTA tears TMEM / smem down
             if (kk >= 1) f7_wait(&bar_vfree[(kk - 1) & 1], ((kk - 1) >> 1) & 1, 5, kk, 0);
+        };
+        if (lane == 0) {
+            if (warp == 20) control(std::integral_constant<int, 0>{});
+            else control(std::integral_constant<int, 1>{});
         }
     } else if (warp >= 16) {        // (warps 16-19; the control warps were taken above)
         // ================================================================ epilogue: TMEM -> slots
