@@ -13,3 +13,8 @@ if [ "${2:-}" = "bwdprof" ]; then
       python bench.py --steps 1 --warmup 2 --no-graph --no-sweep --no-cpu-baseline > $out/bwd_ncu.log 2>&1
   echo "bwd ncu: exit $?"
 fi
+if [ "${2:-}" = "fwdprof" ]; then
+  timeout -s KILL 600 ncu --set full --import-source on --clock-control none -k regex:"sca_fwd_tc4" -s 3 -c 1 -f -o $out/fwd \
+      python bench.py --steps 1 --warmup 2 --no-graph --no-sweep --no-cpu-baseline > $out/fwd_ncu.log 2>&1
+  echo "fwd ncu: exit $?"
+fi
