@@ -248,6 +248,8 @@ class VoxelLayerFunction(Function):
             else:
                 v = torch.addmm(half_of(bv), feat, Wv16.t())
             vimg = ops.value_image(v.view(Bv, S, C), NH)
+            vimg16 = (ops.value_image16(v.view(Bv, S, C), NH, Sh, Sw)
+                      if ops.TC_FORWARD in ops._SORTED16_VARIANT and lib.ver_tc6_supported(Ncam, Sh, Sw, Dh, NP) else None)
             del v
             # sampling_offsets (+) attention_weights once per voxel (:340-343), fp32 out
             if TC_GEMM['logits'] and ops.linear_tc_supported(q, Wcat16):
@@ -261,9 +263,16 @@ class VoxelLayerFunction(Function):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
-                                         _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw, NH, Dh, NP,
-                                         ops._SORTED_VARIANT.get(ops.TC_FORWARD, 0), _stream()))
+        v16 = ops._SORTED16_VARIANT.get(ops.TC_FORWARD)
+        if v16 is not None and lib.ver_tc6_supported(Ncam, Sh, Sw, Dh, NP):
+            # the generations on 16-cell image rows need their own value image (built above, outside the timed span)
+            check(lib.ver_sca_forward_sorted16(_ptr(vimg16), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
+                                               _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw, NH, Dh,
+                                               NP, v16, _stream()))
+        else:
+            check(lib.ver_sca_forward_sorted(_ptr(vimg), _ptr(logits), logits.shape[1], _ptr(vis.rpc), _ptr(order),
+                                             _ptr(smask), _ptr(tile_union), _ptr(slots), B, Ncam, Nq, Sh, Sw, NH, Dh, NP,
+                                             ops._SORTED_VARIANT.get(ops.TC_FORWARD, 0), _stream()))
         if prof is not None:
             e1.record()
             prof.append((e0, e1))

@@ -484,7 +484,7 @@ VER_LAYOUT_TC_IMAGE = 2
 # 'sorted16' / 'sorted16_6': the generations on 16-cell image rows with two builder threads per row -- sca_fwd_tc7_kernel (A
 # operand in TMEM: 389 us against 408 us for sorted4, but it needs its own value image, ver_value_image16_f16, which the backward
 # cannot share) / sca_fwd_tc6_kernel (A in the shared-memory operand, 564 us); 'block': sca_fwd_tc_kernel (4x8x8 voxel blocks)
-TC_FORWARD = 'sorted'
+TC_FORWARD = os.environ.get('VER_TC_FORWARD', 'sorted')      # (the environment override is for A/B runs of bench.py)
 _SORTED_VARIANT = {'sorted': 0, 'sorted3': 3, 'sorted4': 4, 'sorted5': 5, 'sorted16': 0, 'sorted16_6': 0}
 _SORTED16_VARIANT = {'sorted16': 7, 'sorted16_6': 6}      # sca_fwd_tc7_kernel / sca_fwd_tc6_kernel
 
