@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "sampler.cuh"
+#include "tap16.cuh"
 #include "tcgen05.cuh"
 
 namespace {
@@ -496,16 +497,9 @@ sca_fwd_tc7_kernel(const __half* __restrict__ vimg, const float* __restrict__ lo
                     const float ry1 = fmaf(ref.y, fSh, 0.5f) - fpi;               // Y - pi, Y = pixel y + 1
 #pragma unroll
                     for (int p = 0; p < NP; ++p) {
-                        // x: aligned pair base e = 2 floor(X / 2), weights of cells e, e + 1, e + 2
-                        const float X = fminf(fmaxf(rx1 + ox[p], 0.f), xmax);
-                        const float hh = __fmaf_rd(X, 0.5f, kF7Magic);            // 2^23 + e / 2
-                        const float v = fmaf(hh - kF7Magic, -2.f, X) - 1.f;       // u - 1
-                        const float w0 = fmaxf(-v, 0.f), w1 = 1.f - fabsf(v), w2 = fmaxf(v, 0.f);
-                        // y: my image row 2 j + pi that carries weight, clamped (then the tent is 0)
-                        const float t = ry1 + oy[p];
-                        const float jm = fminf(fmaxf(__fmaf_rd(t, 0.5f, kF7Magic), kF7Magic), jtop);
-                        const float d = fmaf(jm - kF7Magic, -2.f, t) - 1.f;       // Y - 1 - (2 j + pi)
-                        const float wy = aw[p] * fmaxf(1.f - fabsf(d), 0.f);
+                        // aligned pair base + three x weights, my image row + its weight: tap16.cuh (checked on the CPU)
+                        const Tap16 tp = tap16(rx1 + ox[p], ry1 + oy[p], aw[p], xmax, jtop);
+                        const float w0 = tp.w0, w1 = tp.w1, w2 = tp.w2, wy = tp.wy, hh = tp.hh, jm = tp.jm;
                         const __half2 h01 = __floats2half2_rn(wy * w0, wy * w1), h2 = __floats2half2_rn(wy * w2, 0.f);
                         const uint32_t hb = __float_as_uint(hh), jb = __float_as_uint(jm);
                         const uint32_t ad = base_adj + ((jb * 16u + hb) << 7);
