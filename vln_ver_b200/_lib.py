@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libver_b200.so')
 
 VER_F32, VER_F16 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class VerError(RuntimeError):
@@ -29,6 +29,12 @@ def _load():
             raise VerError(
                 f'libver_b200.so is missing and could not be built ({e}); '
                 'run `python -m vln_ver_b200.build`') from e
+        # a library exists but could not be rebuilt (no nvcc on this machine, or a compile error): it may be older than
+        # the sources -- say so instead of loading it silently; a changed interface still fails below (missing symbol /
+        # ABI version), a changed kernel body would not
+        import warnings
+        warnings.warn(f'libver_b200.so could not be rebuilt ({type(e).__name__}: {str(e)[:200]}); loading the existing '
+                      f'binary, which may not match the sources', RuntimeWarning, stacklevel=2)
     lib = ctypes.CDLL(LIB_PATH)
     P = c_void_p
     sig = {

@@ -28,6 +28,6 @@ int ver_device_max_smem_optin() {
     return n;
 }
 
-extern "C" int ver_abi_version(void) { return 6; }
+extern "C" int ver_abi_version(void) { return 7; }
 extern "C" const char* ver_last_error(void) { return t_error; }
 extern "C" int64_t ver_launch_count(void) { return g_ver_launches.load(); }
