@@ -132,6 +132,14 @@ def test_half_cache_follows_parameter_versions():
     assert cat2 is not cat1 and torch.equal(cat2[:4], a.detach().half())
     f = F.f32_cat(a, b)
     assert f.dtype == torch.float32 and F.f32_cat(a, b) is f
+    # single-parameter copies are refreshed TOGETHER: the first stale lookup casts every registered copy that is out of date
+    hb = F.half_of(b)
+    with torch.no_grad():
+        a.mul_(0.5)
+        b.add_(2.0)
+    assert torch.equal(F.half_of(a), a.detach().half())
+    assert F._SINGLES[id(b)][2] == (F._GENERATION[0], b._version, b.data_ptr())         # b already refreshed, by a's lookup
+    assert F.half_of(b) is not hb and torch.equal(F.half_of(b), b.detach().half())
 
 
 def test_weight_cache_is_invalidated_explicitly_and_by_hooks():
@@ -168,10 +176,10 @@ def test_weight_cache_is_invalidated_explicitly_and_by_hooks():
     f = FL.half_of(lin.weight)
     assert f is not e and float(f.abs().max()) == 0.0
     # no leak: entries go away with the module
-    n_before = len(FL._HALF_CACHE)
+    n_before = len(FL._HALF_CACHE) + len(FL._SINGLES)
     del lin, opt, a, b, c, d, e, f
     gc.collect()
-    assert len(FL._HALF_CACHE) < max(n_before, 1)
+    assert len(FL._HALF_CACHE) + len(FL._SINGLES) < max(n_before, 1)
 
 
 def test_spatial_shapes_are_read_once():

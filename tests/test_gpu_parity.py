@@ -970,3 +970,26 @@ def test_linear_relu_dropout_backward_fused_gemm(M, N, K, p):
 def _lib_rows(M):
     from vln_ver_b200._lib import lib as _l
     return _l.ver_linear_bwd_colsum_rows(M)
+
+
+@pytest.mark.parametrize('S,NH,Dh', [(196, 8, 96), (35, 4, 32), (70, 2, 64)])
+def test_value_images_are_the_documented_layouts(S, NH, Dh):
+    """ver_value_image_f16 (shared-memory tiled transpose) and ver_value_image16_f16: the tensor-core operand images of the
+    value maps, element for element against their layout definitions in include/ver_b200.h."""
+    Bv = 5
+    g = torch.Generator(device=DEV).manual_seed(S)
+    value = torch.randn(Bv, S, NH * Dh, device=DEV, generator=g).half()
+    SP = (S + 15) // 16 * 16
+    img = ops.value_image(value, NH)                                       # (Bv, NH, Dh/8, SP/8, 8 ch, 8 pix)
+    ref = torch.zeros(Bv, SP, NH, Dh, dtype=torch.float16, device=DEV)
+    ref[:, :S] = value.view(Bv, S, NH, Dh)
+    ref = ref.view(Bv, SP // 8, 8, NH, Dh // 8, 8).permute(0, 3, 4, 1, 5, 2)   # bv, h, cg, pg, c8, p8
+    assert torch.equal(img, ref.contiguous())
+    # 16-cell image rows: cell y * 16 + x + 1 holds pixel (y, x)
+    shapes = {196: (14, 14), 35: (5, 7), 70: (7, 10)}
+    Sh, Sw = shapes[S]
+    img16 = ops.value_image16(value, NH, Sh, Sw)                           # (Bv, NH, Dh/8, 2 Sh, 8 ch, 8 cells)
+    ref16 = torch.zeros(Bv, Sh, 16, NH, Dh, dtype=torch.float16, device=DEV)
+    ref16[:, :, 1:Sw + 1] = value.view(Bv, Sh, Sw, NH, Dh)
+    ref16 = ref16.view(Bv, Sh * 2, 8, NH, Dh // 8, 8).permute(0, 3, 4, 1, 5, 2)
+    assert torch.equal(img16, ref16.contiguous())

@@ -72,10 +72,46 @@ def _cached(kind, params, make):
     return t
 
 
+# fp16 copies of SINGLE parameters are refreshed together: the first stale lookup after a weight update casts every
+# registered copy that is out of date with one multi-tensor kernel (a training step used to launch ~35 separate 5 us
+# cast kernels, inside the captured graph as well).  Entries: id(param) -> [weak reference, fp16 copy, version]; the
+# validity rule is _cached()'s.
+_SINGLES = {}
+
+
+def _refresh_singles():
+    dsts, srcs, done = [], [], []
+    for key, ent in list(_SINGLES.items()):
+        p = ent[0]()
+        if p is None:
+            _SINGLES.pop(key, None)
+            continue
+        ver = (_GENERATION[0], p._version, p.data_ptr())
+        if ent[2] != ver:
+            # a NEW tensor per refresh: a copy that an earlier forward saved for its backward is never overwritten
+            ent[1] = torch.empty(p.shape, dtype=torch.float16, device=p.device)
+            dsts.append(ent[1])
+            srcs.append(p.detach())
+            done.append((ent, ver))
+    if dsts:
+        with torch.no_grad():
+            torch._foreach_copy_(dsts, srcs)
+        for ent, ver in done:
+            ent[2] = ver
+
+
 def half_of(*params):
     """fp16 copy of a parameter (or the row-concatenation of several), refreshed when a parameter changes."""
-    return _cached('f16', params, lambda: params[0].detach().to(torch.float16) if len(params) == 1 else
-                   torch.cat([p.detach() for p in params], 0).to(torch.float16))
+    if len(params) == 1:
+        import weakref
+        p = params[0]
+        ent = _SINGLES.get(id(p))
+        if ent is None or ent[0]() is not p:
+            ent = _SINGLES[id(p)] = [weakref.ref(p, lambda _r, k=id(p): _SINGLES.pop(k, None)), None, None]
+        if ent[2] != (_GENERATION[0], p._version, p.data_ptr()):
+            _refresh_singles()
+        return ent[1]
+    return _cached('f16', params, lambda: torch.cat([p.detach() for p in params], 0).to(torch.float16))
 
 
 def half_t_of(param):
