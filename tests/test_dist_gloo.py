@@ -101,3 +101,25 @@ def test_two_rank_gradient_mean_equals_full_batch(tmp_path):
     for k, g in got['grads'].items():
         ref = sd[k].grad
         assert torch.allclose(g, ref, rtol=1e-9, atol=1e-12), k
+
+
+def test_flat_gradient_buckets_partition_the_buffer():
+    """FlatGradients without a process group: gradients are views of one flat buffer, the buckets are contiguous,
+    cover it exactly and count every parameter once; without a group allreduce_mean_() is the identity."""
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(n)) for n in (1000, 10, 300, 5000, 7, 64)]
+    fg = dist_utils.FlatGradients(params, bucket_bytes=4000, overlap=True)
+    assert not fg.overlap and fg.hooks == []                       # no process group: nothing to overlap
+    assert fg.buckets[0][0] == 0 and fg.buckets[-1][1] == fg.flat.numel() == sum(p.numel() for p in params)
+    assert all(a[1] == b[0] for a, b in zip(fg.buckets, fg.buckets[1:]))
+    assert sum(n for _, _, n in fg.buckets) == len(params)
+    assert all(fg.buckets[fg.bucket_of[i]][0] <= off < fg.buckets[fg.bucket_of[i]][1]
+               for i, off in enumerate([0, 1000, 1010, 1310, 6310, 6317]))
+    fg.zero_()
+    sum((p * (i + 1.0)).sum() for i, p in enumerate(params)).backward()
+    for i, p in enumerate(params):
+        assert p.grad.data_ptr() >= fg.flat.data_ptr() and torch.all(p.grad == i + 1.0)
+    before = fg.flat.clone()
+    assert fg.allreduce_mean_() is fg.flat and torch.equal(fg.flat, before)
+    one = dist_utils.FlatGradients([torch.nn.Parameter(torch.randn(5))])
+    assert len(one.buckets) == 1
